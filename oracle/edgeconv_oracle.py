@@ -1,0 +1,211 @@
+"""CPU oracle for the DGCNN EdgeConv hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is the checker, never the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it.  Nothing under
+``dgcnn.pytorch_b200/`` imports or falls back to it.
+
+It restates, in plain torch ops on whatever device/dtype the inputs carry
+(CPU fp32 for parity, CPU fp64 for gradchecks), the algorithm of the
+reference file ``/root/reference/models/dgcnn.py``:
+
+* ``neg_sqdist`` / ``knn_oracle``      <- ``knn``               dgcnn.py:6-12
+* ``graph_feature_oracle``             <- ``get_graph_feature`` dgcnn.py:15-44
+* ``edgeconv_block_oracle``            <- ``conv{n}`` Sequential + max over k
+                                          dgcnn.py:54-73 applied at :84-98
+* ``DGCNNOracle``                      <- ``class DGCNN``       dgcnn.py:47-103
+
+Parity pin: the reference ships no tests or golden vectors (SURVEY.md §4,
+§8c), so the pins are generated HERE by ``oracle/make_golden.py``, which
+imports the unmodified reference from ``/root/reference``, asserts this
+restatement reproduces it bit-for-bit on CPU, and commits the reference's
+outputs as fixtures under ``tests/golden/``.  ``tests/test_oracle.py`` re-checks
+the oracle against those fixtures on every run.
+
+Extras the reference does not have (needed to test a fused implementation):
+an ``idx=`` override so the EdgeConv arithmetic can be compared on an
+identical neighbour graph, and ``subtract_center=True`` for the canonical
+``(x_j - x_i, x_i)`` edge feature (reference notebook test.ipynb cell 7; the
+``.py`` fork uses ``(x_j, x_i)``, see SURVEY.md §0 trap 1).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+EDGE_WIDTHS = ((3, 64), (64, 64), (64, 128), (128, 256))  # dgcnn.py:54-73
+
+
+# --------------------------------------------------------------------------- kNN
+def neg_sqdist(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,N] -> [B,N,N], D[i,j] = -|xi|^2 + 2 xi.xj - |xj|^2 in the
+    reference's *expanded* evaluation order (dgcnn.py:7-9)."""
+    gram = torch.matmul(x.transpose(2, 1).contiguous(), x)      # :7  x^T x
+    inner = -2 * gram                                           # :7
+    sq = (x ** 2).sum(dim=1, keepdim=True)                      # :8  [B,1,N]
+    return -sq - inner - sq.transpose(2, 1).contiguous()       # :9
+
+
+def knn_oracle(x: torch.Tensor, k: int) -> torch.Tensor:
+    """int64 [B,N,k]: the k largest D per row, nearest first (dgcnn.py:11)."""
+    return neg_sqdist(x).topk(k=k, dim=-1)[1]
+
+
+def exact_sqdist64(x: torch.Tensor) -> torch.Tensor:
+    """fp64 direct-form squared distances [B,N,N]; the tie arbiter of the kNN
+    parity tests (not part of the reference)."""
+    p = x.detach().double().transpose(1, 2)                     # [B,N,C]
+    return ((p[:, :, None, :] - p[:, None, :, :]) ** 2).sum(-1)
+
+
+# ------------------------------------------------------------- neighbour gather
+def gather_rows(pts: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """pts [B,N,C] point-major, idx [B,N,k] (per-cloud indices) -> x_j rows
+    [B,N,k,C] (dgcnn.py:22-34: flat index = idx + b*N into the [B*N, C] view)."""
+    B, N, C = pts.shape
+    k = idx.shape[-1]
+    base = torch.arange(B, device=pts.device).view(B, 1, 1) * N  # :22-23
+    flat = (idx + base).reshape(-1)                              # :25-27
+    return pts.reshape(B * N, C)[flat, :].view(B, N, k, C)       # :33-34
+
+
+def graph_feature_oracle(x: torch.Tensor, k: int = 20, knn_only: bool = False,
+                         disp_only: bool = False, idx: Optional[torch.Tensor] = None,
+                         subtract_center: bool = False) -> torch.Tensor:
+    """dgcnn.py:15-44.  Default: [B,2C,N,k] with channels 0..C-1 = x_j and
+    C..2C-1 = x_i.  knn_only: [B,N,k,C] of x_j.  disp_only: [B,C,N,k] of
+    x_j - x_i.  ``subtract_center`` gives the canonical (x_j - x_i, x_i)."""
+    if x.dim() != 3:
+        raise ValueError("expected x of shape [B, C, N]")
+    B, C, N = x.shape
+    if idx is None:
+        idx = knn_oracle(x, k)                                  # :17
+    pts = x.transpose(2, 1).contiguous()                        # :31  [B,N,C]
+    nbr = gather_rows(pts, idx)                                 # [B,N,k,C]
+    ctr = pts.view(B, N, 1, C).repeat(1, 1, k, 1)               # :35
+    if knn_only:
+        return nbr                                              # :37-38
+    if disp_only:
+        return (nbr - ctr).permute(0, 3, 1, 2).contiguous()     # :39-40
+    first = nbr - ctr if subtract_center else nbr
+    return torch.cat((first, ctr), dim=3).permute(0, 3, 1, 2).contiguous()  # :42
+
+
+# ------------------------------------------------------------- one EdgeConv block
+def edgeconv_block_oracle(x: torch.Tensor, weight: torch.Tensor, gamma: torch.Tensor,
+                          beta: torch.Tensor, running_mean: Optional[torch.Tensor],
+                          running_var: Optional[torch.Tensor], k: int, training: bool,
+                          momentum: float = 0.1, eps: float = 1e-5, slope: float = 0.2,
+                          idx: Optional[torch.Tensor] = None,
+                          subtract_center: bool = False) -> torch.Tensor:
+    """get_graph_feature -> Conv2d(2C,Co,1,bias=False) -> BatchNorm2d ->
+    LeakyReLU(slope) -> max over k (dgcnn.py:84-86 with :54-58).
+    ``weight`` is the Conv2d weight [Co,2C,1,1] (or [Co,2C]).  In training mode
+    running_mean/var are updated in place exactly as nn.BatchNorm2d does."""
+    gf = graph_feature_oracle(x, k=k, idx=idx, subtract_center=subtract_center)
+    z = F.conv2d(gf, weight.reshape(weight.shape[0], -1, 1, 1))
+    z = F.batch_norm(z, running_mean, running_var, gamma, beta, training, momentum, eps)
+    z = F.leaky_relu(z, negative_slope=slope)
+    return z.max(dim=-1, keepdim=False)[0]
+
+
+# ----------------------------------------------------------------- the backbone
+def _block(cin: int, cout: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=1, bias=False),
+                         nn.BatchNorm2d(cout),
+                         nn.LeakyReLU(negative_slope=0.2))
+
+
+class DGCNNOracle(nn.Module):
+    """Same parameters / state_dict keys as the reference ``DGCNN``
+    (conv{1..5}.0.weight, conv{n}.1.*; dgcnn.py:48-78), forward restated from
+    dgcnn.py:80-103.  ``forward(x, idx_list=...)`` runs each EdgeConv layer on a
+    caller-supplied graph; ``last_idx`` records the graphs actually used."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.emb_dims = getattr(args, "emb_dim", None) or getattr(args, "emb_dims")
+        self.k = args.k
+        for n, (c, co) in enumerate(EDGE_WIDTHS, start=1):
+            setattr(self, f"conv{n}", _block(2 * c, co))
+        self.conv5 = _block(sum(co for _, co in EDGE_WIDTHS), self.emb_dims)
+        self.last_idx: List[torch.Tensor] = []
+
+    def edge_layers(self) -> Sequence[nn.Sequential]:
+        return [self.conv1, self.conv2, self.conv3, self.conv4]
+
+    def forward(self, x: torch.Tensor, idx_list: Optional[Sequence[torch.Tensor]] = None,
+                subtract_center: bool = False) -> torch.Tensor:
+        B, _, N = x.shape
+        feats = []
+        self.last_idx = []
+        h = x
+        for layer, seq in enumerate(self.edge_layers()):
+            idx = idx_list[layer] if idx_list is not None else knn_oracle(h, self.k)
+            self.last_idx.append(idx)
+            gf = graph_feature_oracle(h, k=self.k, idx=idx, subtract_center=subtract_center)
+            h = seq(gf).max(dim=-1, keepdim=False)[0]           # :85-86 etc.
+            feats.append(h)
+        cat = torch.cat(feats, dim=1).unsqueeze(-1)             # :100
+        return self.conv5(cat).view(B, -1, N)                   # :102
+
+
+def make_dgcnn_oracle(emb_dim: int = 1024, k: int = 20) -> DGCNNOracle:
+    return DGCNNOracle(SimpleNamespace(emb_dim=emb_dim, k=k))
+
+
+# ------------------------------------------------- synthetic inputs
+def synthetic_xyz(B: int, N: int, seed: int = 1, device="cpu") -> torch.Tensor:
+    """ModelNet40-shape clouds: centred, scaled into the unit ball, [B,3,N]."""
+    g = torch.Generator().manual_seed(seed)
+    p = torch.randn(B, N, 3, generator=g)
+    p = p - p.mean(dim=1, keepdim=True)
+    p = p / p.norm(dim=2).amax(dim=1).view(B, 1, 1)
+    return p.permute(0, 2, 1).contiguous().to(device)
+
+
+def synthetic_features(B: int, C: int, N: int, seed: int = 1, device="cpu") -> torch.Tensor:
+    """Post-activation-like feature clouds [B,C,N]."""
+    g = torch.Generator().manual_seed(seed)
+    return F.leaky_relu(torch.randn(B, C, N, generator=g), 0.2).to(device)
+
+
+# ------------------------------------------------- kNN comparison with the tie rule
+def knn_mismatch_report(x: torch.Tensor, idx_test: torch.Tensor, idx_ref: torch.Tensor,
+                        rel_eps: float = 1e-6) -> dict:
+    """Compare two kNN results as per-row SETS.  A row may differ only where the
+    members that differ are tied: for every j in test\\ref and j' in ref\\test,
+    |d64(i,j) - d64(i,j')| <= rel_eps * (|x_i|^2 + max(|x_j|^2, |x_j'|^2)),
+    with d64 the exact fp64 squared distance (the scale is the magnitude that
+    enters the reference's expanded-form cancellation, dgcnn.py:9).
+    Returns counts; ``bad_rows`` must be 0 for parity."""
+    B, C, N = x.shape
+    d = exact_sqdist64(x.cpu())
+    sq = (x.detach().cpu().double() ** 2).sum(1)                 # [B,N]
+    a = idx_test.cpu().long().sort(dim=-1)[0]
+    r = idx_ref.cpu().long().sort(dim=-1)[0]
+    differing = (a != r).any(-1)                                # [B,N]
+    rows = differing.nonzero(as_tuple=False)
+    bad = 0
+    worst = 0.0
+    for b, i in rows.tolist():
+        sa, sr = set(a[b, i].tolist()), set(r[b, i].tolist())
+        if len(sa) != a.shape[-1]:
+            bad += 1                                            # duplicate neighbour
+            continue
+        only_a, only_r = sorted(sa - sr), sorted(sr - sa)
+        ok = True
+        for j in only_a:
+            for jr in only_r:
+                gap = abs(float(d[b, i, j] - d[b, i, jr]))
+                scale = float(sq[b, i] + max(sq[b, j], sq[b, jr]))
+                worst = max(worst, gap / max(scale, 1e-30))
+                if gap > rel_eps * scale:
+                    ok = False
+        bad += (not ok)
+    return {"rows": B * N, "differing_rows": int(differing.sum()), "bad_rows": bad,
+            "worst_rel_gap": worst}

@@ -1,0 +1,128 @@
+"""The oracle (oracle/edgeconv_oracle.py) against the golden vectors that
+oracle/make_golden.py recorded from the unmodified reference
+(/root/reference/models/dgcnn.py).  CPU only."""
+import glob
+import os
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+import edgeconv_oracle as orc
+from conftest import GOLDEN, load_golden
+
+
+@pytest.fixture(autouse=True)
+def _one_thread():
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)        # fixtures were recorded with one thread
+    yield
+    torch.set_num_threads(n)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "knn_*.npz"))),
+                         ids=os.path.basename)
+def test_knn_matches_reference(path):
+    g = load_golden(os.path.basename(path))
+    idx = orc.knn_oracle(g["x"], g["k"])
+    assert idx.dtype == torch.int64
+    assert torch.equal(idx, g["idx"].long())
+    # self is the nearest neighbour of every point
+    n = g["x"].shape[2]
+    assert torch.equal(idx[..., 0], torch.arange(n).expand_as(idx[..., 0]))
+    rep = orc.knn_mismatch_report(g["x"], idx, g["idx"])
+    assert rep["differing_rows"] == 0 and rep["bad_rows"] == 0
+
+
+def test_graph_feature_layouts():
+    g = load_golden("graph_feature_B2_C5_N48_k6.npz")
+    x, k = g["x"], g["k"]
+    assert torch.equal(orc.graph_feature_oracle(x, k), g["full"])
+    assert torch.equal(orc.graph_feature_oracle(x, k, knn_only=True), g["knn_only"])
+    assert torch.equal(orc.graph_feature_oracle(x, k, disp_only=True), g["disp_only"])
+    # idx override reproduces the same tensor
+    assert torch.equal(orc.graph_feature_oracle(x, k, idx=g["idx"].long()), g["full"])
+    # canonical form differs from the fork form only by the centre subtraction
+    can = orc.graph_feature_oracle(x, k, subtract_center=True)
+    assert torch.equal(can[:, 5:], g["full"][:, 5:])
+    assert torch.equal(can[:, :5], g["disp_only"])
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_block_matches_reference(mode):
+    g = load_golden("block_B3_C6_N80_k7_Co16.npz")
+    x = g["x"].clone().requires_grad_(True)
+    w, ga, be = (g[n].clone().requires_grad_(True) for n in ("weight", "gamma", "beta"))
+    rm, rv = g["running_mean0"].clone(), g["running_var0"].clone()
+    y = orc.edgeconv_block_oracle(x, w, ga, be, rm, rv, g["k"], training=(mode == "train"))
+    (y * g["gout"]).sum().backward()
+    assert torch.equal(y, g[f"{mode}_out"])
+    assert torch.equal(x.grad, g[f"{mode}_dx"])
+    assert torch.equal(w.grad, g[f"{mode}_dw"])
+    assert torch.equal(ga.grad, g[f"{mode}_dgamma"])
+    assert torch.equal(be.grad, g[f"{mode}_dbeta"])
+    assert torch.equal(rm, g[f"{mode}_running_mean"])
+    assert torch.equal(rv, g[f"{mode}_running_var"])
+
+
+def _load_dgcnn():
+    g = load_golden("dgcnn_emb64_k8_B2_N96.npz")
+    net = orc.DGCNNOracle(SimpleNamespace(emb_dim=g["emb_dim"], k=g["k"]))
+    net.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith("sd.")})
+    return g, net
+
+
+def test_dgcnn_train_step_matches_reference():
+    g, net = _load_dgcnn()
+    net.train()
+    x = g["x"].clone().requires_grad_(True)
+    y = net(x)
+    (y * g["gout"]).sum().backward()
+    assert torch.equal(y, g["train_out"])
+    assert torch.equal(x.grad, g["train_dx"])
+    for name, p in net.named_parameters():
+        assert torch.equal(p.grad, g[f"grad.{name}"]), name
+    for name, b in net.named_buffers():
+        assert torch.equal(b, g[f"after.{name}"]), name
+    for n, idx in enumerate(net.last_idx):
+        assert torch.equal(idx, g[f"idx_train{n}"].long())
+
+
+def test_dgcnn_eval_and_idx_override():
+    g, net = _load_dgcnn()
+    # the reference's eval forward was recorded after its one training step
+    net.load_state_dict({k[6:]: v for k, v in g.items() if k.startswith("after.")}, strict=False)
+    net.eval()
+    with torch.no_grad():
+        assert torch.equal(net(g["x"]), g["eval_out"])
+        forced = [g[f"idx_eval{n}"].long() for n in range(4)]
+        assert torch.equal(net(g["x"], idx_list=forced), g["eval_out"])
+
+
+def test_dgcnn_accepts_emb_dims_alias():
+    # main_cls.py:228 defines --emb_dims, models/dgcnn.py:51 reads emb_dim (SURVEY §0 trap 3)
+    net = orc.DGCNNOracle(SimpleNamespace(emb_dims=32, k=4))
+    assert net.conv5[0].weight.shape == (32, 512, 1, 1)
+
+
+def test_split_weight_identity_fp64():
+    """The algebra the fused design rests on: W.[x_j; x_i] =
+    W1.x_j + W2.x_i, and max/min by sign(gamma) commutes with BN+LeakyReLU."""
+    torch.manual_seed(0)
+    B, C, N, k, Co = 2, 5, 40, 6, 7
+    x = torch.randn(B, C, N, dtype=torch.float64)
+    w = torch.randn(Co, 2 * C, dtype=torch.float64)
+    gamma = torch.randn(Co, dtype=torch.float64)
+    beta = torch.randn(Co, dtype=torch.float64)
+    idx = orc.knn_oracle(x, k)
+    ref = orc.edgeconv_block_oracle(x, w, gamma, beta, None, None, k, training=True, idx=idx)
+    pts = x.transpose(1, 2)                                   # [B,N,C]
+    U, V = pts @ w[:, :C].T, pts @ w[:, C:].T                 # [B,N,Co]
+    e = orc.gather_rows(U.contiguous(), idx) + V[:, :, None, :]   # [B,N,k,Co]
+    mean = e.mean(dim=(0, 1, 2))
+    var = e.var(dim=(0, 1, 2), unbiased=False)
+    a = gamma / torch.sqrt(var + 1e-5)
+    b = beta - a * mean
+    sel = torch.where(gamma >= 0, e.max(dim=2)[0], e.min(dim=2)[0])
+    out = torch.nn.functional.leaky_relu(a * sel + b, 0.2).transpose(1, 2)
+    assert torch.allclose(out, ref, rtol=1e-10, atol=1e-12)
