@@ -1,0 +1,12 @@
+"""edgeconv-b200: the DGCNN EdgeConv hot path as hand-written sm_100a kernels.
+
+The package directory is literally ``dgcnn.pytorch_b200`` (not an importable
+dotted name); import it through the ``dgcnn_pytorch_b200`` shim at the repo
+root:  ``import dgcnn_pytorch_b200 as ec``.
+"""
+from . import _lib, ops
+from .dgcnn import DGCNN, edgeconv_block, get_graph_feature, knn
+from .model import ClsHead, DGCNN_cls, cal_loss
+from .ops import edgeconv
+
+__all__ = ["DGCNN", "DGCNN_cls", "ClsHead", "cal_loss", "edgeconv", "edgeconv_block", "get_graph_feature", "knn", "ops", "_lib"]

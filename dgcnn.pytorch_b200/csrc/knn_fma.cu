@@ -1,0 +1,209 @@
+// kNN graph by FP32-FMA distance tiles feeding an on-chip top-k selector.
+// Replaces knn() of /root/reference/models/dgcnn.py:6-12: the [B,N,N] matrix of
+// -|xi|^2 + 2 xi.xj - |xj|^2 is produced tile by tile in registers and consumed
+// immediately by a per-thread heap in shared memory; only idx[B,N,k] reaches HBM.
+//
+// Ranking key.  For a fixed query i the reference's score differs from
+//   s_ij = xi.xj - 0.5*|xj|^2
+// only by the row constant -|xi|^2 and a factor 2, so s_ij ranks identically.
+// The selector orders candidates by the 64-bit key (orderable(s) << 32 | ~j):
+// larger score first, ties towards the smaller index j -- a total order, so the
+// result does not depend on how candidates are split between threads.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int R = 64;         // query rows per CTA
+constexpr int TJ = 64;        // candidates per tile
+constexpr int NT = 128;       // threads per CTA: two per row, one per half of each tile
+constexpr int HALF = TJ / 2;  // candidates a thread scores per tile
+constexpr int KC_MAX = 128;   // channels staged in shared memory per chunk
+
+__device__ __forceinline__ uint32_t orderable(float s) {
+  uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t make_key(float s, int j) {
+  return ((uint64_t)orderable(s) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)j);
+}
+__device__ __forceinline__ float key_score(uint64_t key) {
+  uint32_t u = (uint32_t)(key >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+  return __uint_as_float(u);
+}
+
+// Min-heap of `n` keys at h[0], h[NT], h[2*NT], ... : place `key` starting from the
+// root and sift it down.  The root is the worst of the kept candidates.
+__device__ __forceinline__ void sift_from_root(uint64_t* h, int n, uint64_t key) {
+  int p = 0;
+  while (true) {
+    int c = 2 * p + 1;
+    if (c >= n) break;
+    uint64_t kc = h[c * NT];
+    if (c + 1 < n) {
+      uint64_t k2 = h[(c + 1) * NT];
+      if (k2 < kc) { kc = k2; c = c + 1; }
+    }
+    if (kc >= key) break;
+    h[p * NT] = kc;
+    p = c;
+  }
+  h[p * NT] = key;
+}
+
+__global__ void __launch_bounds__(NT)
+knn_fma_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int k,
+               int KC, int32_t* __restrict__ idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* heap = reinterpret_cast<uint64_t*>(smem_raw);  // [k][NT]
+  float* Qs = reinterpret_cast<float*>(heap + (size_t)k * NT);  // [KC][R]   query rows, c-major
+  float* Cs = Qs + KC * R;                                  // [KC][TJ]  candidate tile, c-major
+  float* hx = Cs + KC * TJ;                                 // [TJ]      -0.5*|xj|^2
+
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * R;
+  const int tid = threadIdx.x;
+  const int r = tid % R;
+  const int h = tid / R;  // warp-uniform: which half of each candidate tile
+  const float* xb = x + (size_t)b * C * N;
+  const float* xxb = xx + (size_t)b * N;
+  uint64_t* my = heap + tid;
+
+  for (int p = 0; p < k; ++p) my[p * NT] = 0ull;
+  uint64_t thr_key = 0ull;
+  float thr_s = -CUDART_INF_F;
+  const int nchunks = (C + KC - 1) / KC;
+
+  for (int j0 = 0; j0 < N; j0 += TJ) {
+    float acc[HALF];
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int c0 = ch * KC;
+      const int kc = min(KC, C - c0);
+      __syncthreads();  // previous tile / chunk fully consumed
+      for (int e = tid; e < kc * TJ; e += NT) {
+        int c = e / TJ, jj = e % TJ;
+        Cs[e] = (j0 + jj < N) ? xb[(size_t)(c0 + c) * N + j0 + jj] : 0.f;
+      }
+      if (nchunks > 1 || j0 == 0) {
+        for (int e = tid; e < kc * R; e += NT) {
+          int c = e / R, rr = e % R;
+          Qs[e] = (row0 + rr < N) ? xb[(size_t)(c0 + c) * N + row0 + rr] : 0.f;
+        }
+      }
+      if (ch == 0 && tid < TJ) hx[tid] = (j0 + tid < N) ? -0.5f * xxb[j0 + tid] : -CUDART_INF_F;
+      __syncthreads();
+      if (ch == 0) {
+#pragma unroll
+        for (int u = 0; u < HALF; ++u) acc[u] = hx[h * HALF + u];
+      }
+#pragma unroll 2
+      for (int c = 0; c < kc; ++c) {
+        const float q = Qs[c * R + r];
+        const float4* cp = reinterpret_cast<const float4*>(Cs + c * TJ + h * HALF);
+#pragma unroll
+        for (int v = 0; v < HALF / 4; ++v) {
+          float4 t = cp[v];  // same address in every lane: broadcast
+          acc[4 * v + 0] = fmaf(q, t.x, acc[4 * v + 0]);
+          acc[4 * v + 1] = fmaf(q, t.y, acc[4 * v + 1]);
+          acc[4 * v + 2] = fmaf(q, t.z, acc[4 * v + 2]);
+          acc[4 * v + 3] = fmaf(q, t.w, acc[4 * v + 3]);
+        }
+      }
+    }
+    // selection: candidates arrive in ascending j, so ">=" on the score followed by
+    // the exact key compare keeps the (score, smaller-j) total order.
+    const int jbase = j0 + h * HALF;
+#pragma unroll
+    for (int u = 0; u < HALF; ++u) {
+      const float s = acc[u];
+      if (jbase + u < N && s >= thr_s) {
+        const uint64_t key = make_key(s, jbase + u);
+        if (key > thr_key) {
+          sift_from_root(my, k, key);
+          thr_key = my[0];
+          thr_s = key_score(thr_key);
+        }
+      }
+    }
+  }
+
+  // merge the two halves of each row into the h == 0 thread's heap
+  __syncthreads();
+  if (h == 0) {
+    const uint64_t* other = heap + tid + R;
+    for (int p = 0; p < k; ++p) {
+      const uint64_t key = other[p * NT];
+      if (key > thr_key) {
+        sift_from_root(my, k, key);
+        thr_key = my[0];
+      }
+    }
+    // heap sort in place: afterwards my[0..k-1] is descending (nearest first)
+    for (int n = k - 1; n > 0; --n) {
+      const uint64_t last = my[n * NT];
+      my[n * NT] = my[0];
+      sift_from_root(my, n, last);
+    }
+    const int row = row0 + r;
+    if (row < N) {
+      int32_t* out = idx + ((size_t)b * N + row) * k;
+      for (int p = 0; p < k; ++p) {
+        uint32_t j = 0xFFFFFFFFu - (uint32_t)(my[p * NT] & 0xFFFFFFFFull);
+        out[p] = (int32_t)min(j, (uint32_t)(N - 1));  // only NaN input can leave an empty slot
+      }
+    }
+  }
+}
+
+__global__ void sqnorms_kernel(const float* __restrict__ x, int C, int N, long long M,
+                               float* __restrict__ xx) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  long long b = m / N;
+  int n = (int)(m - b * N);
+  const float* p = x + (size_t)b * C * N + n;
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) {
+    float v = p[(size_t)c * N];
+    s = fmaf(v, v, s);
+  }
+  xx[m] = s;
+}
+
+}  // namespace
+
+extern "C" int ecb200_sqnorms(const float* x, int B, int C, int N, float* xx, void* stream) {
+  ECB_REQUIRE(x && xx, "ecb200_sqnorms: null pointer");
+  ECB_REQUIRE(B >= 1 && C >= 1 && N >= 1, "ecb200_sqnorms: bad shape B=%d C=%d N=%d", B, C, N);
+  long long M = (long long)B * N;
+  sqnorms_kernel<<<(unsigned)ecb200::ceil_div64(M, 256), 256, 0, (cudaStream_t)stream>>>(x, C, N, M,
+                                                                                        xx);
+  ECB_LAUNCH_CHECK("sqnorms_kernel");
+  return ECB200_OK;
+}
+
+extern "C" int ecb200_knn(const float* x, const float* xx, int B, int C, int N, int k,
+                          int32_t* idx, void* stream) {
+  ECB_REQUIRE(x && xx && idx, "ecb200_knn: null pointer");
+  ECB_REQUIRE(B >= 1 && C >= 1 && N >= 1, "ecb200_knn: bad shape B=%d C=%d N=%d", B, C, N);
+  ECB_REQUIRE(B <= 65535, "ecb200_knn: B=%d exceeds 65535 clouds per call", B);
+  // same trigger as Tensor.topk in the reference (dgcnn.py:11): k must not exceed N
+  ECB_REQUIRE(k >= 1 && k <= N, "ecb200_knn: k=%d out of range for N=%d (selected index k out of range)", k, N);
+  ECB_REQUIRE(k <= ECB200_MAX_K, "ecb200_knn: k=%d exceeds ECB200_MAX_K=%d", k, ECB200_MAX_K);
+  const int KC = C < KC_MAX ? C : KC_MAX;
+  const size_t smem = (size_t)k * NT * sizeof(uint64_t) + (size_t)KC * (R + TJ) * sizeof(float) +
+                      TJ * sizeof(float);
+  static thread_local bool seen[ecb200::kMaxDevices] = {};
+  if (ecb200::first_use_on_device(seen)) {
+    const size_t smem_max = (size_t)ECB200_MAX_K * NT * sizeof(uint64_t) +
+                            (size_t)KC_MAX * (R + TJ) * sizeof(float) + TJ * sizeof(float);
+    ECB_CUDA(cudaFuncSetAttribute(knn_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_max));
+  }
+  dim3 grid(ecb200::ceil_div(N, R), B);
+  knn_fma_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(x, xx, C, N, k, KC, idx);
+  ECB_LAUNCH_CHECK("knn_fma_kernel");
+  return ECB200_OK;
+}

@@ -1,0 +1,132 @@
+"""Drop-in for the reference's ``models/dgcnn.py`` (knn, get_graph_feature, DGCNN).
+
+Same names, call signatures, return layouts, parameter names and state_dict keys
+as /root/reference/models/dgcnn.py, so ``models/model_partseg.py`` (Net),
+``models/layers.py`` (PositionEmbedding) and the training scripts run unchanged
+on top of it -- but every tensor operation of the EdgeConv path is a hand-written
+sm_100a kernel reached through the C ABI (see ops.py / include/edgeconv_b200.h).
+CUDA tensors only; CPU tensors raise (the CPU path is the reference itself).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def knn(x: torch.Tensor, k: int) -> torch.Tensor:
+    """models/dgcnn.py:6-12.  x [B,C,N] -> int64 [B,N,k]: indices of the k nearest
+    points (self included) by the reference's -|xi|^2 + 2 xi.xj - |xj|^2 score,
+    nearest first; equal scores resolve to the smaller index."""
+    return ops.knn_op(_as_f32(x), int(k)).long()
+
+
+def _as_f32(x: torch.Tensor) -> torch.Tensor:
+    # under autocast the reference's matmul would run in fp16; the fused
+    # path always computes in fp32, so half inputs are widened here
+    if x.dim() != 3:
+        raise ValueError(f"expected x of shape [B, C, N], got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("edgeconv_b200 runs on CUDA tensors only: there is no CPU fallback "
+                           f"(got a tensor on {x.device}); the CPU path is the reference itself")
+    return x if x.dtype == torch.float32 else x.float()
+
+
+def get_graph_feature(x: torch.Tensor, k: int = 20, knn_only: bool = False,
+                      disp_only: bool = False, idx: Optional[torch.Tensor] = None,
+                      dim9: bool = False, subtract_center: bool = False) -> torch.Tensor:
+    """models/dgcnn.py:15-44.  Default: [B,2C,N,k] = (x_j, x_i) along channels;
+    ``knn_only`` -> [B,N,k,C] of x_j; ``disp_only`` -> [B,C,N,k] of x_j - x_i.
+    Differentiable w.r.t. x (gather + centre copy), not w.r.t. the indices.
+
+    Extras kept from upstream DGCNN, which main_semseg.py expects: ``idx`` (reuse a
+    graph), ``dim9`` (build the graph on channels 6: of a 9-channel input) and
+    ``subtract_center`` for the canonical (x_j - x_i, x_i) feature."""
+    x = _as_f32(x)
+    if idx is None:
+        src = x[:, 6:] if dim9 else x
+        idx32 = ops.knn_op(src.contiguous(), int(k))
+    else:
+        idx32 = idx.to(torch.int32)
+    if knn_only:
+        mode = ops.GF_KNN_ONLY
+    elif disp_only:
+        mode = ops.GF_DISP_ONLY
+    else:
+        mode = ops.GF_CONCAT_CENTERED if subtract_center else ops.GF_CONCAT
+    return ops.graph_feature_op(x, idx32, mode)
+
+
+def _edge_block(cin: int, cout: int) -> nn.Sequential:
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=1, bias=False),
+                         nn.BatchNorm2d(cout),
+                         nn.LeakyReLU(negative_slope=0.2, inplace=True))
+
+
+def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
+                   idx: Optional[torch.Tensor] = None, subtract_center: bool = False):
+    """One EdgeConv layer = ``block(get_graph_feature(x, k)).max(-1)[0]`` of the
+    reference (models/dgcnn.py:84-86), fused.  ``block`` is the reference's own
+    ``nn.Sequential(Conv2d(2C,Co,1,bias=False), BatchNorm2d | SyncBatchNorm,
+    LeakyReLU)``; its parameters and buffers are read at call time, so
+    ``SyncBatchNorm.convert_sync_batchnorm`` and DDP keep working.
+    Returns (out [B,Co,N], idx int32 [B,N,k])."""
+    conv, bn, act = block[0], block[1], block[2]
+    if conv.bias is not None or tuple(conv.kernel_size) != (1, 1):
+        raise RuntimeError("edgeconv_block expects a bias-free 1x1 Conv2d")
+    x = _as_f32(x)
+    if idx is None:
+        idx = ops.knn_op(x.detach().contiguous(), int(k))
+    group = 0
+    if isinstance(bn, nn.SyncBatchNorm) and bn.training and torch.distributed.is_available() \
+            and torch.distributed.is_initialized():
+        pg = bn.process_group if bn.process_group is not None else torch.distributed.group.WORLD
+        if torch.distributed.get_world_size(pg) > 1:
+            group = ops.register_group(pg)
+    slope = float(getattr(act, "negative_slope", 0.0))
+    out = ops.edgeconv(x, idx, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                       bn.num_batches_tracked, bn.training, bn.momentum, bn.eps, slope,
+                       subtract_center, group)
+    return out, idx
+
+
+class DGCNN(nn.Module):
+    """models/dgcnn.py:47-103: four EdgeConv layers on dynamic (feature-space) kNN
+    graphs, concatenated and embedded by conv5.  ``args.k`` neighbours;
+    ``args.emb_dim`` (or upstream's ``args.emb_dims``) embedding width.
+    forward: x [B,3,N] -> [B, emb_dim, N]."""
+
+    def __init__(self, args):
+        super().__init__()
+        emb = getattr(args, "emb_dim", None)
+        if emb is None:
+            emb = getattr(args, "emb_dims")
+        self.emb_dims = emb
+        self.k = args.k
+        self.subtract_center = bool(getattr(args, "subtract_center", False))
+        self.conv1 = _edge_block(3 * 2, 64)
+        self.conv2 = _edge_block(64 * 2, 64)
+        self.conv3 = _edge_block(64 * 2, 128)
+        self.conv4 = _edge_block(128 * 2, 256)
+        self.conv5 = _edge_block(512, self.emb_dims)
+        self.record_idx = False
+        self.last_idx: List[torch.Tensor] = []
+
+    def forward(self, x: torch.Tensor, idx_list=None) -> torch.Tensor:
+        batch_size, _, num_points = x.size()
+        feats = []
+        if self.record_idx:
+            self.last_idx = []
+        h = x
+        for layer, block in enumerate((self.conv1, self.conv2, self.conv3, self.conv4)):
+            forced = None if idx_list is None else idx_list[layer].to(torch.int32)
+            h, idx = edgeconv_block(h, block, self.k, idx=forced,
+                                    subtract_center=self.subtract_center)
+            if self.record_idx:
+                self.last_idx.append(idx)
+            feats.append(h)
+        h = torch.cat(feats, dim=1).unsqueeze(-1)        # [B,512,N,1]  dgcnn.py:100
+        return self.conv5(h).view(batch_size, -1, num_points)   # dgcnn.py:102

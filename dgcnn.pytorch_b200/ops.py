@@ -1,0 +1,334 @@
+"""torch.library custom ops over the C ABI (include/edgeconv_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every piece of
+arithmetic on the EdgeConv path is a kernel of libedgeconv_b200.so.  CPU tensors
+are rejected -- the CPU path is the oracle under oracle/, which this package never
+imports.
+
+Ops (namespace ``edgeconv_b200``):
+  knn(x, k) -> int32 [B,N,k]                       reference knn(), models/dgcnn.py:6-12
+  graph_feature(x, idx, mode) -> edge tensor       get_graph_feature(), dgcnn.py:15-44
+  edgeconv_fwd(...) -> out [B,Co,N] (+ saved)      conv{n} + max over k, dgcnn.py:54-73,:84-98
+  edgeconv_bwd(...) -> dx, dW, dgamma, dbeta       their autograd
+"""
+from __future__ import annotations
+
+from ctypes import c_void_p
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import _lib
+
+GF_CONCAT, GF_KNN_ONLY, GF_DISP_ONLY, GF_CONCAT_CENTERED = 0, 1, 2, 3
+MAX_K = 64
+
+# torch.distributed process groups cannot travel through an op schema: ops take an
+# integer handle into this table (0 = no cross-rank BatchNorm statistics).
+_GROUPS = {}
+
+
+def register_group(group) -> int:
+    """Handle for a process group whose ranks share BatchNorm statistics
+    (SyncBatchNorm semantics, main_partseg_dist.py:189)."""
+    if group is None:
+        group = dist.group.WORLD
+    for h, g in _GROUPS.items():
+        if g is group:
+            return h
+    h = len(_GROUPS) + 1
+    _GROUPS[h] = group
+    return h
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream(t: Tensor):
+    return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _check_cuda_f32(name: str, t: Tensor, dims: Optional[int] = None):
+    if not t.is_cuda:
+        raise RuntimeError(f"edgeconv_b200: {name} must be a CUDA tensor (no CPU fallback; "
+                           f"got device {t.device})")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"edgeconv_b200: {name} must be float32, got {t.dtype}")
+    if dims is not None and t.dim() != dims:
+        raise ValueError(f"edgeconv_b200: {name} must have {dims} dimensions, got shape "
+                         f"{tuple(t.shape)}")
+
+
+# ------------------------------------------------------------------------------ kNN
+@torch.library.custom_op("edgeconv_b200::knn", mutates_args=(), device_types="cuda")
+def knn_op(x: Tensor, k: int) -> Tensor:
+    _check_cuda_f32("x", x, 3)
+    B, C, N = x.shape
+    if k > N or k < 1:
+        # same trigger as Tensor.topk in the reference (dgcnn.py:11)
+        raise RuntimeError(f"selected index k out of range (k={k}, N={N})")
+    if k > MAX_K:
+        raise RuntimeError(f"edgeconv_b200: k={k} exceeds the selector limit {MAX_K}")
+    x = x.contiguous()
+    with torch.cuda.device(x.device):
+        xx = torch.empty(B * N, device=x.device, dtype=torch.float32)
+        idx = torch.empty(B, N, k, device=x.device, dtype=torch.int32)
+        st = _stream(x)
+        _lib.call("ecb200_sqnorms", _ptr(x), B, C, N, _ptr(xx), st)
+        _lib.call("ecb200_knn", _ptr(x), _ptr(xx), B, C, N, k, _ptr(idx), st)
+    return idx
+
+
+@knn_op.register_fake
+def _(x, k):
+    B, C, N = x.shape
+    return x.new_empty((B, N, k), dtype=torch.int32)
+
+
+# ------------------------------------------------------------------- graph feature
+def _gf_shape(B, C, N, k, mode):
+    if mode == GF_KNN_ONLY:
+        return (B, N, k, C)
+    if mode == GF_DISP_ONLY:
+        return (B, C, N, k)
+    return (B, 2 * C, N, k)
+
+
+@torch.library.custom_op("edgeconv_b200::graph_feature", mutates_args=(), device_types="cuda")
+def graph_feature_op(x: Tensor, idx: Tensor, mode: int) -> Tensor:
+    _check_cuda_f32("x", x, 3)
+    B, C, N = x.shape
+    k = idx.shape[-1]
+    x = x.contiguous()
+    idx = idx.contiguous()
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (B, N, k)
+    with torch.cuda.device(x.device):
+        out = torch.empty(_gf_shape(B, C, N, k, mode), device=x.device, dtype=torch.float32)
+        _lib.call("ecb200_graph_feature", _ptr(x), _ptr(idx), B, C, N, k, mode, _ptr(out), _stream(x))
+    return out
+
+
+@graph_feature_op.register_fake
+def _(x, idx, mode):
+    B, C, N = x.shape
+    return x.new_empty(_gf_shape(B, C, N, idx.shape[-1], mode))
+
+
+@torch.library.custom_op("edgeconv_b200::graph_feature_bwd", mutates_args=(), device_types="cuda")
+def graph_feature_bwd_op(gout: Tensor, idx: Tensor, C: int, mode: int) -> Tensor:
+    B, N, k = idx.shape
+    gout = gout.contiguous().float()
+    with torch.cuda.device(gout.device):
+        dx = torch.empty(B, C, N, device=gout.device, dtype=torch.float32)
+        _lib.call("ecb200_graph_feature_bwd", _ptr(gout), _ptr(idx.contiguous()), B, C, N, k, mode,
+                  _ptr(dx), _stream(gout))
+    return dx
+
+
+@graph_feature_bwd_op.register_fake
+def _(gout, idx, C, mode):
+    B, N, k = idx.shape
+    return gout.new_empty((B, C, N))
+
+
+def _gf_setup(ctx, inputs, output):
+    x, idx, mode = inputs
+    ctx.save_for_backward(idx)
+    ctx.C = x.shape[1]
+    ctx.mode = mode
+
+
+def _gf_backward(ctx, gout):
+    (idx,) = ctx.saved_tensors
+    return graph_feature_bwd_op(gout, idx, ctx.C, ctx.mode), None, None
+
+
+graph_feature_op.register_autograd(_gf_backward, setup_context=_gf_setup)
+
+
+# ------------------------------------------------------------------ fused EdgeConv
+@torch.library.custom_op("edgeconv_b200::edgeconv_fwd", mutates_args=(), device_types="cuda")
+def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor,
+                    running_mean: Optional[Tensor], running_var: Optional[Tensor],
+                    use_batch_stats: bool, eps: float, slope: float, subtract_center: bool,
+                    group: int, save_for_bwd: bool) -> List[Tensor]:
+    """Returns [out, sel, arg, esum, Y, Wcat, affine, stats]; ``affine`` is [4,Co] =
+    (mean, invstd, a, b).  Everything after ``out`` exists for the backward pass."""
+    _check_cuda_f32("x", x, 3)
+    B, C, N = x.shape
+    k = idx.shape[-1]
+    Co = weight.shape[0]
+    if weight.numel() != Co * 2 * C:
+        raise RuntimeError(f"edgeconv_b200: weight {tuple(weight.shape)} does not match 2*C = {2 * C}")
+    if Co % 4 != 0:
+        raise RuntimeError(f"edgeconv_b200: output channels must be a multiple of 4, got {Co}")
+    x = x.contiguous()
+    idx = idx.contiguous()
+    w = weight.detach().reshape(Co, 2 * C).contiguous().float()
+    gamma_c, beta_c = gamma.detach().contiguous().float(), beta.detach().contiguous().float()
+    dev = x.device
+    M = B * N
+    with torch.cuda.device(dev):
+        st = _stream(x)
+        f32 = dict(device=dev, dtype=torch.float32)
+        Wcat = torch.empty(2 * Co, C, **f32)
+        Y = torch.empty(M, 2 * Co, **f32)
+        sel = torch.empty(M, Co, **f32)
+        arg = torch.empty(M, Co, device=dev, dtype=torch.uint8)
+        esum = torch.empty(M, Co, **f32) if save_for_bwd else None
+        stats = torch.zeros(2 * Co + 1, device=dev, dtype=torch.float64)
+        affine = torch.empty(4, Co, **f32)
+        mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * Co * r) for r in range(4))
+        out = torch.empty(B, Co, N, **f32)
+        _lib.call("ecb200_pack_weight", _ptr(w), Co, C, int(subtract_center), _ptr(Wcat), st)
+        _lib.call("ecb200_point_gemm", _ptr(x), _ptr(Wcat), B, C, N, 2 * Co, _ptr(Y), st)
+        _lib.call("ecb200_edge_gather", _ptr(Y), _ptr(idx), _ptr(gamma_c), B, N, k, Co, _ptr(sel),
+                  _ptr(arg), _ptr(esum), _ptr(stats) if use_batch_stats else None, st)
+        if use_batch_stats and group:
+            # the one exchange step of the path: [sum e, sum e^2, count] over the ranks
+            dist.all_reduce(stats, group=_GROUPS[group])
+        _lib.call("ecb200_bn_finalize", _ptr(stats), _ptr(gamma_c), _ptr(beta_c),
+                  None if use_batch_stats else _ptr(running_mean),
+                  None if use_batch_stats else _ptr(running_var),
+                  int(use_batch_stats), float(eps), Co, mean, invstd, a, b, st)
+        _lib.call("ecb200_edge_apply", _ptr(sel), a, b, float(slope), B, N, Co, _ptr(out), st)
+    if esum is None:
+        esum = sel.new_empty(0)
+    return [out, sel, arg, esum, Y, Wcat, affine, stats]
+
+
+@edgeconv_fwd_op.register_fake
+def _(x, idx, weight, gamma, beta, running_mean, running_var, use_batch_stats, eps, slope,
+      subtract_center, group, save_for_bwd):
+    B, C, N = x.shape
+    Co = weight.shape[0]
+    M = B * N
+    f = x.new_empty
+    return [f((B, Co, N)), f((M, Co)), f((M, Co), dtype=torch.uint8),
+            f((M, Co)) if save_for_bwd else f((0,)), f((M, 2 * Co)), f((2 * Co, C)),
+            f((4, Co)), f((2 * Co + 1,), dtype=torch.float64)]
+
+
+@torch.library.custom_op("edgeconv_b200::edgeconv_bwd", mutates_args=(), device_types="cuda")
+def edgeconv_bwd_op(gout: Tensor, x: Tensor, idx: Tensor, sel: Tensor, arg: Tensor, esum: Tensor,
+                    Y: Tensor, Wcat: Tensor, affine: Tensor, stats: Tensor, use_batch_stats: bool,
+                    slope: float, subtract_center: bool, group: int) -> List[Tensor]:
+    """-> [dx [B,C,N], dW [Co,2C], dgamma [Co], dbeta [Co]]"""
+    B, C, N = x.shape
+    k = idx.shape[-1]
+    Co = sel.shape[1]
+    M = B * N
+    dev = x.device
+    gout = gout.contiguous().float()
+    with torch.cuda.device(dev):
+        st = _stream(x)
+        f32 = dict(device=dev, dtype=torch.float32)
+        g = torch.empty(M, Co, **f32)
+        bstats = torch.zeros(2 * Co, device=dev, dtype=torch.float64)
+        mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * Co * r) for r in range(4))
+        _lib.call("ecb200_bwd_prep", _ptr(gout), _ptr(sel), a, b, mean, invstd,
+                  float(slope), B, N, Co, _ptr(g), _ptr(bstats), st)
+        if use_batch_stats and group:
+            bglobal = bstats.clone()
+            dist.all_reduce(bglobal, group=_GROUPS[group])
+        else:
+            bglobal = bstats
+        dgamma = torch.empty(Co, **f32)
+        dbeta = torch.empty(Co, **f32)
+        cc = torch.empty(2, Co, **f32)
+        c1, c2 = c_void_p(cc.data_ptr()), c_void_p(cc.data_ptr() + 4 * Co)
+        _lib.call("ecb200_bwd_finalize", _ptr(bstats), _ptr(bglobal),
+                  c_void_p(stats.data_ptr() + 8 * 2 * Co), a, invstd,
+                  int(use_batch_stats), Co, _ptr(dgamma), _ptr(dbeta), c1, c2, st)
+        dY = torch.empty(M, 2 * Co, **f32)
+        rowptr = src = None
+        if use_batch_stats:
+            rowptr = torch.empty(M + 1, device=dev, dtype=torch.int32)
+            src = torch.empty(M * k, device=dev, dtype=torch.int32)
+            cursor = torch.empty(M, device=dev, dtype=torch.int32)
+            _lib.call("ecb200_reverse_graph", _ptr(idx), B, N, k, _ptr(rowptr), _ptr(src), _ptr(cursor), st)
+        _lib.call("ecb200_bwd_dense", _ptr(Y), _ptr(rowptr), _ptr(src), mean, c1, c2,
+                  int(use_batch_stats), B, N, Co, _ptr(dY), st)
+        _lib.call("ecb200_bwd_scatter", _ptr(g), _ptr(esum), _ptr(arg), _ptr(idx), a, mean,
+                  c1, c2, B, N, k, Co, _ptr(dY), st)
+        dx = torch.empty(B, C, N, **f32)
+        dWcat = torch.empty(2 * Co, C, **f32)
+        dW = torch.empty(Co, 2 * C, **f32)
+        _lib.call("ecb200_gemm_dx", _ptr(dY), _ptr(Wcat), B, C, N, 2 * Co, _ptr(dx), st)
+        _lib.call("ecb200_gemm_dw", _ptr(dY), _ptr(x), B, C, N, 2 * Co, _ptr(dWcat), st)
+        _lib.call("ecb200_unpack_weight_grad", _ptr(dWcat), Co, C, int(subtract_center), _ptr(dW), st)
+    return [dx, dW, dgamma, dbeta]
+
+
+@edgeconv_bwd_op.register_fake
+def _(gout, x, idx, sel, arg, esum, Y, Wcat, affine, stats, use_batch_stats, slope,
+      subtract_center, group):
+    B, C, N = x.shape
+    Co = sel.shape[1]
+    f = x.new_empty
+    return [f((B, C, N)), f((Co, 2 * C)), f((Co,)), f((Co,))]
+
+
+def _ec_setup(ctx, inputs, output):
+    (x, idx, weight, gamma, beta, _rm, _rv, use_batch_stats, _eps, slope, subtract_center, group,
+     save_for_bwd) = inputs
+    out, sel, arg, esum, Y, Wcat, affine, stats = output
+    if not save_for_bwd:
+        raise RuntimeError("edgeconv_b200: forward ran with save_for_bwd=False but a gradient "
+                           "is required")
+    ctx.save_for_backward(x, idx, sel, arg, esum, Y, Wcat, affine, stats)
+    ctx.cfg = (use_batch_stats, slope, subtract_center, group)
+    ctx.wshape = tuple(weight.shape)
+    ctx.set_materialize_grads(False)
+
+
+def _ec_backward(ctx, grads):
+    gout = grads[0]
+    n_in = 13
+    if gout is None:
+        return (None,) * n_in
+    x, idx, sel, arg, esum, Y, Wcat, affine, stats = ctx.saved_tensors
+    use_batch_stats, slope, subtract_center, group = ctx.cfg
+    dx, dW, dgamma, dbeta = edgeconv_bwd_op(gout, x, idx, sel, arg, esum, Y, Wcat, affine, stats,
+                                            use_batch_stats, slope, subtract_center, group)
+    return (dx, None, dW.view(ctx.wshape), dgamma, dbeta) + (None,) * (n_in - 5)
+
+
+edgeconv_fwd_op.register_autograd(_ec_backward, setup_context=_ec_setup)
+
+
+@torch.library.custom_op("edgeconv_b200::bn_update_running",
+                         mutates_args=("running_mean", "running_var", "num_batches_tracked"),
+                         device_types="cuda")
+def bn_update_running_op(stats: Tensor, running_mean: Optional[Tensor], running_var: Optional[Tensor],
+                         num_batches_tracked: Optional[Tensor], momentum: float) -> None:
+    """The in-place side effect of a training-mode BatchNorm2d forward (running statistics,
+    num_batches_tracked), from the global [sum e, sum e^2, count] buffer."""
+    Co = (stats.numel() - 1) // 2
+    with torch.cuda.device(stats.device):
+        _lib.call("ecb200_bn_update_running", _ptr(stats), Co, float(momentum), _ptr(running_mean),
+                  _ptr(running_var), _ptr(num_batches_tracked), _stream(stats))
+
+
+def edgeconv(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor,
+             running_mean: Optional[Tensor], running_var: Optional[Tensor],
+             num_batches_tracked: Optional[Tensor], training: bool, momentum: Optional[float] = 0.1,
+             eps: float = 1e-5, slope: float = 0.2, subtract_center: bool = False,
+             group: int = 0) -> Tensor:
+    """Fused EdgeConv block on a given kNN graph:
+    max_k LeakyReLU(BatchNorm2d(Conv2d_1x1([x_j (- x_i) ; x_i])))  ->  [B, Co, N]
+    (models/dgcnn.py:84-86 with :54-58).  BatchNorm semantics follow nn.BatchNorm2d:
+    batch statistics when ``training`` or when no running statistics exist."""
+    use_batch_stats = bool(training or running_mean is None or running_var is None)
+    update_running = bool(training and running_mean is not None)
+    need_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (x, weight, gamma, beta))
+    mom = -1.0 if momentum is None else float(momentum)
+    res = edgeconv_fwd_op(x, idx, weight, gamma, beta, running_mean, running_var, use_batch_stats,
+                          float(eps), float(slope), bool(subtract_center), int(group), bool(need_grad))
+    if update_running:
+        bn_update_running_op(res[-1].detach(), running_mean, running_var, num_batches_tracked, mom)
+    return res[0]

@@ -1,0 +1,189 @@
+/*
+ * edgeconv_b200.h -- C ABI of libedgeconv_b200.so: the DGCNN EdgeConv hot path
+ * (kNN graph + neighbour gather + edge MLP + BatchNorm + LeakyReLU + max over k)
+ * as hand-written sm_100a CUDA kernels.
+ *
+ * This is the drop-in boundary for /root/reference/models/dgcnn.py.  The
+ * reference is pure Python calling torch ops; a maintainer binds these entry
+ * points with ctypes behind the same Python signatures:
+ *
+ *   knn(x, k)                         models/dgcnn.py:6-12   -> ecb200_sqnorms + ecb200_knn
+ *   get_graph_feature(x, k, ...)      models/dgcnn.py:15-44  -> ecb200_graph_feature(_bwd)
+ *   conv{n}(...) ; x.max(dim=-1)      models/dgcnn.py:54-73, :84-98
+ *                                      -> ecb200_pack_weight, ecb200_point_gemm,
+ *                                         ecb200_edge_gather, ecb200_bn_finalize,
+ *                                         ecb200_edge_apply  (forward)
+ *                                         ecb200_bwd_* + ecb200_gemm_dx/dw (backward)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into memory owned by the caller
+ *     (PyTorch's allocator); the library never allocates, frees or synchronises,
+ *     it only enqueues kernels on `stream` (a cudaStream_t passed as void*).
+ *   - all floating-point tensors are contiguous fp32 unless stated; "stats"
+ *     accumulators are fp64.  Neighbour indices are int32, local to their cloud
+ *     (0..N-1); the Python `knn()` widens to int64 as the reference returns.
+ *   - x is the reference's channel-major layout [B, C, N].  Point-major arrays
+ *     are [M, *] with M = B*N and row m = b*N + n.
+ *   - return value: 0 = success, otherwise an ECB200_ERR_* code; the message is
+ *     available from ecb200_last_error() (thread-local).  No C++ exception
+ *     crosses the boundary.  There is no CPU fallback.
+ *   - re-entrant: no global mutable state; safe to call from one host thread
+ *     per GPU (nn.DataParallel, main_cls.py:62) with the device already current.
+ */
+#ifndef EDGECONV_B200_H_
+#define EDGECONV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define ECB200_VERSION 100            /* major*100 + minor */
+#define ECB200_MAX_K 64               /* neighbours per point supported by the selector */
+
+enum {
+  ECB200_OK = 0,
+  ECB200_ERR_ARG = 1,                 /* bad shape / null pointer / unsupported size */
+  ECB200_ERR_CUDA = 2                 /* a CUDA runtime call or launch failed */
+};
+
+/* graph-feature output layouts, get_graph_feature() models/dgcnn.py:37-42 */
+enum {
+  ECB200_GF_CONCAT = 0,               /* [B,2C,N,k]: (x_j , x_i)            dgcnn.py:42 */
+  ECB200_GF_KNN_ONLY = 1,             /* [B,N,k,C] : x_j                    dgcnn.py:37-38 */
+  ECB200_GF_DISP_ONLY = 2,            /* [B,C,N,k] : x_j - x_i              dgcnn.py:39-40 */
+  ECB200_GF_CONCAT_CENTERED = 3       /* [B,2C,N,k]: (x_j - x_i , x_i)      test.ipynb cell 7 */
+};
+
+int ecb200_version(void);
+const char* ecb200_last_error(void);
+
+/* ---- kNN graph: replaces knn(), models/dgcnn.py:6-12 ------------------------------ */
+
+/* xx[m] = sum_c x[b,c,n]^2  (dgcnn.py:8).  x [B,C,N] -> xx [B*N]. */
+int ecb200_sqnorms(const float* x, int B, int C, int N, float* xx, void* stream);
+
+/* idx[b,i,0..k-1] = the k points j of cloud b with the largest
+ * -|x_i|^2 + 2 x_i.x_j - |x_j|^2 (dgcnn.py:9-11), nearest first; ties broken
+ * towards the smaller j.  FP32 FMA distance tiles feeding an on-chip top-k
+ * selector: the [B,N,N] matrix is never written.  Requires 1 <= k <= min(N, 64). */
+int ecb200_knn(const float* x, const float* xx, int B, int C, int N, int k,
+               int32_t* idx, void* stream);
+
+/* Tensor-core variant for feature-space layers (C % 8 == 0, C <= 256): tcgen05
+ * kind::tf32 tiles with 3xTF32 error compensation, accumulators in TMEM, same
+ * selector.  Needs the point-major hi/lo operands made by ecb200_split_tf32.
+ * (declared now so the binding is stable; returns ECB200_ERR_ARG if the build
+ * does not carry the kernel) */
+int ecb200_split_tf32(const float* x, int B, int C, int N, float* hi, float* lo,
+                      float* xx, void* stream);
+int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, int B, int C, int N,
+                  int k, int32_t* idx, void* stream);
+
+/* ---- materialised graph feature: replaces get_graph_feature(), dgcnn.py:15-44 ------ */
+int ecb200_graph_feature(const float* x, const int32_t* idx, int B, int C, int N, int k,
+                         int mode, float* out, void* stream);
+/* dx[B,C,N] (zero-filled by the callee) = gradient of the above w.r.t. x */
+int ecb200_graph_feature_bwd(const float* gout, const int32_t* idx, int B, int C, int N, int k,
+                             int mode, float* dx, void* stream);
+
+/* ---- EdgeConv forward: replaces conv{n} + max over k, dgcnn.py:54-73, :84-98 ------- */
+
+/* Wcat[2Co,C]: rows 0..Co-1 = W[:, :C], rows Co..2Co-1 = W[:, C:]  (minus W[:, :C] when
+ * subtract_center, i.e. the canonical (x_j - x_i, x_i) edge feature).  W is the
+ * Conv2d weight [Co, 2C] (dgcnn.py:55). */
+int ecb200_pack_weight(const float* W, int Co, int C, int subtract_center, float* Wcat,
+                       void* stream);
+
+/* Y[M,2Co] = [U | V],  U = x^T W1^T,  V = x^T W2'^T : the one dense per-point
+ * GEMM that replaces the k-fold 1x1 convolution over [B,2C,N,k]. */
+int ecb200_point_gemm(const float* x, const float* Wcat, int B, int C, int N, int Co2,
+                      float* Y, void* stream);
+
+/* For every point i and channel o, over its k neighbours j: e = U[idx[i,j],o] + V[i,o];
+ *   sel[i,o]  = max_j e if gamma[o] >= 0 else min_j e       (what survives BN+LeakyReLU+max)
+ *   arg[i,o]  = the slot j that attained it                 (for the scatter backward)
+ *   esum[i,o] = sum_j e                                      (optional, may be NULL; backward)
+ *   stats[0..Co-1] += sum_ij e, stats[Co..2Co-1] += sum_ij e^2, stats[2Co] += B*N*k
+ *             (fp64 [2Co+1], optional, may be NULL; caller zero-fills.  The edge count
+ *             rides along so that ONE all-reduce of this buffer makes all three global.)
+ * Co % 4 == 0, Co <= 2048. */
+int ecb200_edge_gather(const float* Y, const int32_t* idx, const float* gamma, int B, int N,
+                       int k, int Co, float* sel, uint8_t* arg, float* esum, double* stats,
+                       void* stream);
+
+/* BatchNorm2d statistics -> per-channel affine (nn.BatchNorm2d semantics, dgcnn.py:56):
+ * training: count = stats[2Co], mean = S1/count, var = S2/count - mean^2 (biased); `stats` is
+ *           GLOBAL (already all-reduced under SyncBatchNorm).
+ * eval:     mean/var = running_mean/running_var (read only).
+ * out: mean, invstd, a = gamma*invstd, b = beta - a*mean  (all [Co] fp32). */
+int ecb200_bn_finalize(const double* stats, const float* gamma, const float* beta,
+                       const float* running_mean, const float* running_var, int training,
+                       float eps, int Co, float* mean, float* invstd, float* a, float* b,
+                       void* stream);
+
+/* The in-place side effect of a training-mode BatchNorm2d forward:
+ * running_mean <- (1-f)*running_mean + f*mean, running_var <- (1-f)*running_var + f*var_unbiased,
+ * num_batches_tracked += 1; f = momentum, or 1/num_batches_tracked (after the increment) when
+ * momentum < 0 (nn.BatchNorm2d(momentum=None)).  Any of the three pointers may be NULL. */
+int ecb200_bn_update_running(const double* stats, int Co, float momentum, float* running_mean,
+                             float* running_var, int64_t* num_batches_tracked, void* stream);
+
+/* out[b,o,n] = leaky_relu(a[o]*sel[m,o] + b[o], slope)   ([M,Co] -> [B,Co,N]) */
+int ecb200_edge_apply(const float* sel, const float* a, const float* b, float slope, int B,
+                      int N, int Co, float* out, void* stream);
+
+/* ---- EdgeConv backward ------------------------------------------------------------ */
+
+/* g[m,o] = gout[b,o,n] * (a*sel+b > 0 ? 1 : slope);  bstats[0..Co-1] += sum g (d beta),
+ * bstats[Co..2Co-1] += sum g*(sel-mean)*invstd (d gamma); fp64, caller zero-fills. */
+int ecb200_bwd_prep(const float* gout, const float* sel, const float* a, const float* b,
+                    const float* mean, const float* invstd, float slope, int B, int N, int Co,
+                    float* g, double* bstats, void* stream);
+
+/* dgamma/dbeta (fp32) from the LOCAL sums; c1 = a*dbeta_g/count, c2 = a*dgamma_g*invstd/count
+ * from the GLOBAL sums (equal to local on one GPU); count = *count_dev, the global edge count
+ * the forward left in stats[2Co].  training == 0 -> c1 = c2 = 0 (count_dev may be NULL). */
+int ecb200_bwd_finalize(const double* bstats_local, const double* bstats_global,
+                        const double* count_dev,
+                        const float* a, const float* invstd, int training, int Co,
+                        float* dgamma, float* dbeta, float* c1, float* c2, void* stream);
+
+/* Reverse (destination-major) kNN graph for the dense BatchNorm terms:
+ * rowptr[M+1] (global offsets), src[M*k] (global source point ids).
+ * `cursor` is an int32 [M] scratch array. */
+int ecb200_reverse_graph(const int32_t* idx, int B, int N, int k, int32_t* rowptr,
+                         int32_t* src, int32_t* cursor, void* stream);
+
+/* dY[:, :Co] (= dU) <- the dense BatchNorm-backward terms through the reverse graph
+ * (training), or zeros (eval). */
+int ecb200_bwd_dense(const float* Y, const int32_t* rowptr, const int32_t* src,
+                     const float* mean, const float* c1, const float* c2, int training, int B,
+                     int N, int Co, float* dY, void* stream);
+
+/* dY[:, Co:] (= dV) and the sparse scatter of a*g into dU rows through the arg slots. */
+int ecb200_bwd_scatter(const float* g, const float* esum, const uint8_t* arg,
+                       const int32_t* idx, const float* a, const float* mean, const float* c1,
+                       const float* c2, int B, int N, int k, int Co, float* dY, void* stream);
+
+/* dx[B,C,N] = dY . Wcat ;  dWcat[2Co,C] = dY^T . x^T (callee zero-fills) */
+int ecb200_gemm_dx(const float* dY, const float* Wcat, int B, int C, int N, int Co2, float* dx,
+                   void* stream);
+int ecb200_gemm_dw(const float* dY, const float* x, int B, int C, int N, int Co2, float* dWcat,
+                   void* stream);
+/* dW[Co,2C] from dWcat (inverse of ecb200_pack_weight, including subtract_center) */
+int ecb200_unpack_weight_grad(const float* dWcat, int Co, int C, int subtract_center, float* dW,
+                              void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDGECONV_B200_H_ */

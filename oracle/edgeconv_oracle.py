@@ -158,6 +158,46 @@ def make_dgcnn_oracle(emb_dim: int = 1024, k: int = 20) -> DGCNNOracle:
     return DGCNNOracle(SimpleNamespace(emb_dim=emb_dim, k=k))
 
 
+class DGCNNClsOracle(nn.Module):
+    """DGCNN-cls for the CPU reference arm of bench.py: the reference backbone
+    (restated above) + upstream DGCNN's classification head (global max+avg pool ->
+    2*emb -> 512 -> 256 -> classes), as BASELINE.md §3.4 defines the headline model.
+    Same submodule names as the product's ``DGCNN_cls`` so state_dicts interchange."""
+
+    def __init__(self, args, output_channels: int = 40):
+        super().__init__()
+        self.backbone = DGCNNOracle(args)
+        emb = self.backbone.emb_dims
+        head = nn.Module()
+        head.linear1 = nn.Linear(emb * 2, 512, bias=False)
+        head.bn6 = nn.BatchNorm1d(512)
+        head.dp1 = nn.Dropout(p=float(getattr(args, "dropout", 0.5)))
+        head.linear2 = nn.Linear(512, 256)
+        head.bn7 = nn.BatchNorm1d(256)
+        head.dp2 = nn.Dropout(p=float(getattr(args, "dropout", 0.5)))
+        head.linear3 = nn.Linear(256, output_channels)
+        self.head = head
+
+    def forward(self, x: torch.Tensor, idx_list=None) -> torch.Tensor:
+        h = self.head
+        f = self.backbone(x, idx_list=idx_list)
+        b = f.size(0)
+        f = torch.cat((F.adaptive_max_pool1d(f, 1).view(b, -1),
+                       F.adaptive_avg_pool1d(f, 1).view(b, -1)), 1)
+        f = h.dp1(F.leaky_relu(h.bn6(h.linear1(f)), negative_slope=0.2))
+        f = h.dp2(F.leaky_relu(h.bn7(h.linear2(f)), negative_slope=0.2))
+        return h.linear3(f)
+
+
+def smoothed_ce_oracle(pred: torch.Tensor, gold: torch.Tensor, eps: float = 0.2) -> torch.Tensor:
+    """Label-smoothed cross entropy of the reference (loss.py:4-21)."""
+    gold = gold.contiguous().view(-1)
+    n_class = pred.size(1)
+    one_hot = torch.zeros_like(pred).scatter(1, gold.view(-1, 1), 1)
+    one_hot = one_hot * (1 - eps) + (1 - one_hot) * eps / (n_class - 1)
+    return -(one_hot * F.log_softmax(pred, dim=1)).sum(dim=1).mean()
+
+
 # ------------------------------------------------- synthetic inputs (SURVEY §8d)
 def synthetic_xyz(B: int, N: int, seed: int = 1, device="cpu") -> torch.Tensor:
     """ModelNet40-shape clouds: centred, scaled into the unit ball, [B,3,N]."""

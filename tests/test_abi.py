@@ -1,0 +1,98 @@
+"""Host-side checks that need no GPU: the C-ABI library loads, exports every symbol
+include/edgeconv_b200.h declares with the arity the ctypes table binds, argument
+validation works without touching the device, and the Python mirror keeps the
+reference's interface (names, state_dict keys, error behaviour)."""
+import ctypes
+import os
+import re
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "edgeconv_b200.h")
+
+
+@pytest.fixture(scope="module")
+def ec():
+    import __graft_entry__ as ge
+    ge.build()
+    import dgcnn_pytorch_b200 as ec
+    return ec
+
+
+def _declared():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"\b(?:int|const char\*)\s+(ecb200_\w+)\s*\(([^)]*)\)\s*;", text):
+        args = m.group(2).strip()
+        decls[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return decls
+
+
+def test_header_symbols_exported_and_bound(ec):
+    decls = _declared()
+    assert len(decls) >= 20
+    lib = ctypes.CDLL(ec._lib.LIB_PATH)
+    for name, nargs in decls.items():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        if name in ("ecb200_version", "ecb200_last_error"):
+            continue
+        assert name in ec._lib.SIGNATURES, f"{name} has no ctypes binding"
+        assert len(ec._lib.SIGNATURES[name]) == nargs, name
+    assert set(ec._lib.SIGNATURES) <= set(decls)
+
+
+def test_version_and_error_string(ec):
+    assert ec._lib.version() == 100
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    with pytest.raises(RuntimeError, match="null pointer"):
+        ec._lib.call("ecb200_knn", None, None, 1, 3, 8, 2, None, None)
+    one = ctypes.c_void_p(16)
+    with pytest.raises(RuntimeError, match="out of range"):
+        ec._lib.call("ecb200_knn", one, one, 1, 3, 8, 9, one, None)       # k > N, like topk
+    with pytest.raises(RuntimeError, match="ECB200_MAX_K"):
+        ec._lib.call("ecb200_knn", one, one, 1, 3, 4096, 65, one, None)
+    with pytest.raises(RuntimeError, match="multiple of 4"):
+        ec._lib.call("ecb200_edge_gather", one, one, one, 1, 8, 2, 6, one, one, None, None, None)
+
+
+def test_cpu_tensors_are_rejected_not_served(ec):
+    x = torch.randn(2, 3, 16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ec.knn(x, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ec.get_graph_feature(x, k=4)
+    net = ec.DGCNN(SimpleNamespace(emb_dim=32, k=4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(x)
+    with pytest.raises(ValueError):
+        ec.get_graph_feature(torch.randn(3, 16), k=4)
+
+
+def test_module_mirrors_reference_interface(ec):
+    import edgeconv_oracle as orc
+    args = SimpleNamespace(emb_dim=48, k=6)
+    ours, ref = ec.DGCNN(args), orc.DGCNNOracle(args)
+    sd_o, sd_r = ours.state_dict(), ref.state_dict()
+    assert list(sd_o.keys()) == list(sd_r.keys())
+    assert all(sd_o[k].shape == sd_r[k].shape for k in sd_o)
+    ours.load_state_dict(sd_r)                       # reference checkpoints load unchanged
+    assert ours.k == 6 and ours.emb_dims == 48
+    assert ec.DGCNN(SimpleNamespace(emb_dims=16, k=4)).conv5[0].weight.shape == (16, 512, 1, 1)
+    # SyncBatchNorm conversion swaps conv{n}[1] in place; the fused forward reads it from there
+    conv = torch.nn.SyncBatchNorm.convert_sync_batchnorm(ours)
+    assert isinstance(conv.conv1[1], torch.nn.SyncBatchNorm)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dgcnn.pytorch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "edgeconv_oracle" not in text and "/root/reference" not in text.replace(
+                    "/root/reference/models/dgcnn.py", ""), f

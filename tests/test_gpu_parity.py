@@ -1,0 +1,320 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the golden
+vectors recorded from the unmodified reference.  Run on the B200 box: -m gpu.
+
+Tolerances (BASELINE.json north_star):
+  * kNN indices: identical per-row sets, except rows whose differing members are
+    tied within 1e-6 relative distance (see edgeconv_oracle.knn_mismatch_report);
+  * EdgeConv outputs and gradients: |ours - ref| <= 1e-4 * max|ref| element-wise.
+"""
+import glob
+import os
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+import edgeconv_oracle as orc
+from conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+TIE_EPS = 1e-6
+
+
+@pytest.fixture(scope="module")
+def ec():
+    import dgcnn_pytorch_b200 as ec
+    return ec
+
+
+@pytest.fixture(autouse=True)
+def _fp32_oracle():
+    # the oracle is CPU fp32; keep any on-device torch math at full precision too
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def assert_rel(ours, ref, rel=REL, what=""):
+    ours, ref = ours.detach().cpu().double(), ref.detach().cpu().double()
+    assert ours.shape == ref.shape, f"{what}: shape {tuple(ours.shape)} vs {tuple(ref.shape)}"
+    scale = ref.abs().max().item()
+    err = (ours - ref).abs().max().item()
+    assert err <= rel * max(scale, 1e-30), f"{what}: max|diff| {err:.3e} > {rel} * {scale:.3e}"
+
+
+def check_knn(ec, x, k, idx_ref=None):
+    idx = ec.knn(x.to(dev()), k)
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (x.shape[0], x.shape[2], k)
+    if idx_ref is None:
+        idx_ref = orc.knn_oracle(x, k)
+    rep = orc.knn_mismatch_report(x, idx.cpu(), idx_ref, rel_eps=TIE_EPS)
+    assert rep["bad_rows"] == 0, rep
+    # nearest-first order: distances along k are non-decreasing (up to fp32 noise)
+    d = orc.exact_sqdist64(x).gather(2, idx.cpu())
+    scale = (x.double() ** 2).sum(1).max().item()
+    assert ((d[..., 1:] - d[..., :-1]) >= -4e-6 * max(scale, 1e-30)).all()
+    return rep
+
+
+# ------------------------------------------------------------------------- kNN
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "knn_*.npz"))),
+                         ids=os.path.basename)
+def test_knn_golden(ec, path):
+    g = load_golden(os.path.basename(path))
+    check_knn(ec, g["x"], g["k"], g["idx"].long())
+
+
+@pytest.mark.parametrize("B,C,N,k,kind", [
+    (32, 3, 1024, 20, "xyz"),        # BASELINE config 1, layer 1
+    (4, 64, 1024, 20, "feat"),       # config 1, layers 2-3
+    (2, 128, 1024, 20, "feat"),      # config 1, layer 4
+    (4, 3, 2048, 40, "xyz"),         # config 2
+    (1, 128, 2048, 40, "feat"),
+    (2, 3, 4096, 20, "xyz"),         # sem-seg shape (graph on the xyz slice)
+    (3, 9, 333, 16, "feat"),         # ragged: N not a multiple of any tile
+    (2, 200, 150, 33, "feat"),       # C above one shared-memory chunk, odd k
+    (5, 3, 64, 64, "xyz"),           # k == N == ECB200_MAX_K
+    (2, 7, 5, 5, "feat"),            # tiny cloud, k == N
+    (1, 3, 1, 1, "xyz"),             # a single point
+])
+def test_knn_vs_oracle(ec, B, C, N, k, kind):
+    x = orc.synthetic_xyz(B, N, seed=B + N) if kind == "xyz" else orc.synthetic_features(B, C, N, seed=C + N)
+    rep = check_knn(ec, x, k)
+    assert rep["differing_rows"] <= max(2, rep["rows"] // 200), rep
+
+
+def test_knn_self_is_first_and_deterministic(ec):
+    x = orc.synthetic_xyz(4, 512, seed=9).to(dev())
+    a, b = ec.knn(x, 20), ec.knn(x, 20)
+    assert torch.equal(a, b)
+    assert torch.equal(a[..., 0], torch.arange(512, device=dev()).expand(4, 512))
+
+
+def test_knn_ties_lattice_and_duplicates(ec):
+    # integer lattice: massive exact ties; every returned set must still be a valid kNN set
+    g = torch.stack(torch.meshgrid(*[torch.arange(6.0)] * 3, indexing="ij"), 0).reshape(1, 3, -1)
+    check_knn(ec, g, 10)
+    # 5 % exact duplicates (ModelNet40 / S3DIS have them)
+    x = orc.synthetic_xyz(2, 400, seed=5)
+    x[:, :, 380:] = x[:, :, :20]
+    check_knn(ec, x, 20)
+    # tie rule: equal scores resolve to the smaller index
+    idx = ec.knn(torch.zeros(1, 3, 40, device=dev()), 7)
+    assert torch.equal(idx[0], torch.arange(7, device=dev()).expand(40, 7))
+
+
+def test_knn_errors_match_reference_triggers(ec):
+    x = torch.randn(2, 3, 16, device=dev())
+    with pytest.raises(RuntimeError, match="out of range"):
+        ec.knn(x, 17)                        # topk raises the same way (dgcnn.py:11)
+    with pytest.raises(ValueError):
+        ec.knn(x[0], 4)                      # reference fails on the 3-d unpack (dgcnn.py:18)
+
+
+# --------------------------------------------------------------- graph feature
+def test_graph_feature_golden_all_layouts(ec):
+    g = load_golden("graph_feature_B2_C5_N48_k6.npz")
+    x, k, idx = g["x"].to(dev()), g["k"], g["idx"].to(dev())
+    assert torch.equal(ec.get_graph_feature(x, k, idx=idx).cpu(), g["full"])
+    assert torch.equal(ec.get_graph_feature(x, k, knn_only=True, idx=idx).cpu(), g["knn_only"])
+    assert torch.equal(ec.get_graph_feature(x, k, disp_only=True, idx=idx).cpu(), g["disp_only"])
+    # with its own kNN (no ties in this fixture) the result is identical too
+    assert torch.equal(ec.get_graph_feature(x, k).cpu(), g["full"])
+
+
+@pytest.mark.parametrize("mode", ["full", "knn_only", "disp_only", "centered"])
+def test_graph_feature_backward(ec, mode):
+    x = orc.synthetic_features(2, 6, 70, seed=31)
+    k = 9
+    idx = orc.knn_oracle(x, k)
+    kw = dict(knn_only=mode == "knn_only", disp_only=mode == "disp_only",
+              subtract_center=mode == "centered")
+    xr = x.clone().requires_grad_(True)
+    yr = orc.graph_feature_oracle(xr, k, idx=idx, **kw)
+    w = torch.randn(yr.shape, generator=torch.Generator().manual_seed(1))
+    (yr * w).sum().backward()
+    xg = x.to(dev()).requires_grad_(True)
+    yg = ec.get_graph_feature(xg, k, idx=idx.to(dev()), **kw)
+    (yg * w.to(dev())).sum().backward()
+    assert torch.equal(yg.detach().cpu(), yr.detach())
+    assert_rel(xg.grad, xr.grad, what=f"graph_feature dx ({mode})")
+
+
+# ------------------------------------------------------------- one EdgeConv block
+def run_block(ec, x, w, gamma, beta, rm, rv, k, training, idx, gout, subtract_center=False):
+    d = dev()
+    xg = x.to(d).requires_grad_(True)
+    wg, gg, bg = (t.to(d).requires_grad_(True) for t in (w, gamma, beta))
+    rmg, rvg = rm.to(d), rv.to(d)
+    nbt = torch.zeros((), dtype=torch.int64, device=d)
+    y = ec.edgeconv(xg, idx.to(d).int(), wg, gg, bg, rmg, rvg, nbt, training, 0.1, 1e-5, 0.2,
+                    subtract_center)
+    (y * gout.to(d)).sum().backward()
+    return y, xg.grad, wg.grad, gg.grad, bg.grad, rmg, rvg, nbt
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_block_golden(ec, mode):
+    g = load_golden("block_B3_C6_N80_k7_Co16.npz")
+    y, dx, dw, dga, dbe, rm, rv, nbt = run_block(
+        ec, g["x"], g["weight"], g["gamma"], g["beta"], g["running_mean0"], g["running_var0"],
+        g["k"], mode == "train", g["idx"], g["gout"])
+    assert_rel(y, g[f"{mode}_out"], what="out")
+    assert_rel(dx, g[f"{mode}_dx"], what="dx")
+    assert_rel(dw, g[f"{mode}_dw"], what="dW")
+    assert_rel(dga, g[f"{mode}_dgamma"], what="dgamma")
+    assert_rel(dbe, g[f"{mode}_dbeta"], what="dbeta")
+    assert_rel(rm, g[f"{mode}_running_mean"], rel=1e-5, what="running_mean")
+    assert_rel(rv, g[f"{mode}_running_var"], rel=1e-5, what="running_var")
+    assert int(nbt) == (1 if mode == "train" else 0)
+
+
+@pytest.mark.parametrize("B,C,N,k,Co,sub", [
+    (4, 3, 1024, 20, 64, False),      # config 1 layer 1 (xyz -> 64)
+    (2, 64, 1024, 20, 64, False),     # layer 2
+    (2, 64, 512, 20, 128, False),     # layer 3 widths
+    (1, 128, 512, 20, 256, False),    # layer 4 widths
+    (2, 64, 256, 40, 64, True),       # canonical (x_j - x_i, x_i), k = 40
+    (3, 5, 77, 6, 12, False),         # ragged sizes, Co % 8 != 0
+    (2, 9, 130, 8, 40, True),
+])
+@pytest.mark.parametrize("training", [True, False])
+def test_block_vs_oracle(ec, B, C, N, k, Co, sub, training):
+    gen = torch.Generator().manual_seed(B * 1000 + C + N + Co)
+    x = orc.synthetic_xyz(B, N, seed=N) if C == 3 else orc.synthetic_features(B, C, N, seed=C + N)
+    w = torch.randn(Co, 2 * C, generator=gen) / (2 * C) ** 0.5
+    gamma = torch.randn(Co, generator=gen) * 0.5 + 1.0
+    gamma[::3] *= -1.0                              # min path
+    beta = torch.randn(Co, generator=gen) * 0.3
+    rm = torch.randn(Co, generator=gen) * 0.2
+    rv = torch.rand(Co, generator=gen) + 0.5
+    gout = torch.randn(B, Co, N, generator=gen)
+    idx = orc.knn_oracle(x, k)
+    xr = x.clone().requires_grad_(True)
+    wr, gr, br = (t.clone().requires_grad_(True) for t in (w, gamma, beta))
+    rmr, rvr = rm.clone(), rv.clone()
+    yr = orc.edgeconv_block_oracle(xr, wr, gr, br, rmr, rvr, k, training, idx=idx, subtract_center=sub)
+    (yr * gout).sum().backward()
+    y, dx, dw, dga, dbe, rmg, rvg, _ = run_block(ec, x, w, gamma, beta, rm, rv, k, training, idx, gout, sub)
+    assert_rel(y, yr, what="out")
+    assert_rel(dx, xr.grad, what="dx")
+    assert_rel(dw, wr.grad, what="dW")
+    assert_rel(dga, gr.grad, what="dgamma")
+    assert_rel(dbe, br.grad, what="dbeta")
+    assert_rel(rmg, rmr, rel=1e-5, what="running_mean")
+    assert_rel(rvg, rvr, rel=1e-5, what="running_var")
+
+
+def test_block_no_grad_and_inference_mode(ec):
+    g = load_golden("block_B3_C6_N80_k7_Co16.npz")
+    d = dev()
+    with torch.no_grad():
+        y = ec.edgeconv(g["x"].to(d), g["idx"].to(d), g["weight"].to(d), g["gamma"].to(d),
+                        g["beta"].to(d), g["running_mean0"].to(d), g["running_var0"].to(d), None,
+                        False)
+    assert_rel(y, g["eval_out"], what="eval out (no_grad)")
+
+
+# ------------------------------------------------------------------ the backbone
+def _dgcnn_pair(ec, g):
+    args = SimpleNamespace(emb_dim=g["emb_dim"], k=g["k"])
+    net = ec.DGCNN(args)
+    net.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith("sd.")})
+    return net.to(dev())
+
+
+def test_dgcnn_golden_train_step(ec):
+    g = load_golden("dgcnn_emb64_k8_B2_N96.npz")
+    net = _dgcnn_pair(ec, g).train()
+    net.record_idx = True
+    x = g["x"].to(dev()).requires_grad_(True)
+    y = net(x)
+    (y * g["gout"].to(dev())).sum().backward()
+    # the dynamic graphs must be the reference's (no ties in this fixture) ...
+    for n, idx in enumerate(net.last_idx):
+        assert torch.equal(idx.cpu().sort(-1)[0], g[f"idx_train{n}"].sort(-1)[0]), f"layer {n} graph"
+    # ... and then values, gradients and BatchNorm buffers agree
+    assert_rel(y, g["train_out"], what="out")
+    assert_rel(x.grad, g["train_dx"], what="dx")
+    for name, p in net.named_parameters():
+        assert_rel(p.grad, g[f"grad.{name}"], what=f"grad {name}")
+    for name, b in net.named_buffers():
+        if name.endswith("num_batches_tracked"):
+            assert int(b) == int(g[f"after.{name}"]), name
+        else:
+            assert_rel(b, g[f"after.{name}"], rel=1e-5, what=name)
+
+
+def test_dgcnn_golden_eval(ec):
+    g = load_golden("dgcnn_emb64_k8_B2_N96.npz")
+    net = _dgcnn_pair(ec, g)
+    net.load_state_dict({k[6:]: v for k, v in g.items() if k.startswith("after.")}, strict=False)
+    net.eval()
+    with torch.no_grad():
+        y = net(g["x"].to(dev()))
+    assert_rel(y, g["eval_out"], what="eval out")
+
+
+def test_dgcnn_config1_shape_vs_oracle_on_same_graphs(ec):
+    """BASELINE config 1 shapes (N=1024, k=20, emb 1024) on a batch the CPU oracle
+    finishes in seconds; the oracle is driven with OUR per-layer graphs so the EdgeConv
+    arithmetic is compared exactly, and the graphs are compared separately."""
+    torch.manual_seed(5)
+    args = SimpleNamespace(emb_dim=1024, k=20)
+    net = ec.DGCNN(args).to(dev()).train()
+    net.record_idx = True
+    ref = orc.DGCNNOracle(args)
+    ref.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
+    ref.train()
+    x = orc.synthetic_xyz(4, 1024, seed=1)
+    xg = x.to(dev()).requires_grad_(True)
+    y = net(xg)
+    y.square().mean().backward()
+    idx_list = [i.long().cpu() for i in net.last_idx]
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr, idx_list=idx_list)
+    yr.square().mean().backward()
+    assert_rel(y, yr, what="out")
+    assert_rel(xg.grad, xr.grad, what="dx")
+    for (n1, p1), (n2, p2) in zip(net.named_parameters(), ref.named_parameters()):
+        assert_rel(p1.grad, p2.grad, rel=2e-4 if n1.startswith("conv5") else REL, what=f"grad {n1}")
+    # layer-1 graph against the oracle's own kNN on the same input
+    rep = orc.knn_mismatch_report(x, idx_list[0], orc.knn_oracle(x, 20), rel_eps=TIE_EPS)
+    assert rep["bad_rows"] == 0, rep
+
+
+def test_full_size_properties(ec):
+    """BASELINE config 2 size (B=32, N=2048, k=40): properties that need no oracle run."""
+    d = dev()
+    B, N, k = 32, 2048, 40
+    x = orc.synthetic_xyz(B, N, seed=2).to(d)
+    idx = ec.knn(x, k)
+    assert torch.equal(idx[..., 0], torch.arange(N, device=d).expand(B, N))      # self first
+    assert int(idx.min()) >= 0 and int(idx.max()) < N
+    srt = idx.sort(-1)[0]
+    assert bool((srt[..., 1:] != srt[..., :-1]).all())                            # no duplicates
+    # permutation equivariance of the graph: permuting the points permutes the sets
+    perm = torch.randperm(N, device=d)
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(N, device=d)
+    idx_p = ec.knn(x[:, :, perm].contiguous(), k)              # neighbours in permuted numbering
+    back = perm[idx_p][:, inv]                                 # rows and values in original numbering
+    same = (back.sort(-1)[0] == srt).all(-1).float().mean().item()
+    assert same > 0.999, same
+    # fused block == materialised path (graph feature kernel + torch conv/bn/max) on the device
+    torch.manual_seed(0)
+    Co = 64
+    w = torch.randn(Co, 6, device=d) * 0.4
+    gamma = torch.randn(Co, device=d)
+    beta = torch.randn(Co, device=d)
+    y = ec.edgeconv(x[:4], idx[:4].int(), w, gamma, beta, None, None, None, True)
+    gf = ec.get_graph_feature(x[:4], k, idx=idx[:4])
+    z = torch.nn.functional.conv2d(gf, w.view(Co, 6, 1, 1))
+    z = torch.nn.functional.batch_norm(z, None, None, gamma, beta, True, 0.1, 1e-5)
+    yr = torch.nn.functional.leaky_relu(z, 0.2).max(-1)[0]
+    assert_rel(y, yr, what="fused vs materialised")
