@@ -347,7 +347,7 @@ def run_b200(a):
     def e2e_step(i):
         x = host_x[i % npool].to(dev, non_blocking=True)
         y = host_y[i % npool].to(dev, non_blocking=True)
-        return float(step(x, y))            # .item(): D2H of the loss, every step
+        return step(x, y).item()            # D2H of the loss, every step
     for i in range(2):
         e2e_step(i)
     barrier()

@@ -1,7 +1,7 @@
 // kNN graph by FP32-FMA distance tiles feeding an on-chip top-k selector.
 // Replaces knn() of /root/reference/models/dgcnn.py:6-12: the [B,N,N] matrix of
 // -|xi|^2 + 2 xi.xj - |xj|^2 is produced tile by tile in registers and consumed
-// immediately by a per-thread heap in shared memory; only idx[B,N,k] reaches HBM.
+// immediately by the per-row top-k selector of topk_select.cuh; only idx[B,N,k] reaches HBM.
 //
 // Ranking key.  For a fixed query i the reference's score differs from
 //   s_ij = xi.xj - 0.5*|xj|^2
@@ -12,6 +12,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "topk_select.cuh"
 
 namespace {
 
@@ -20,47 +21,17 @@ constexpr int TJ = 64;        // candidates per tile
 constexpr int NT = 128;       // threads per CTA: two per row, one per half of each tile
 constexpr int HALF = TJ / 2;  // candidates a thread scores per tile
 constexpr int KC_MAX = 128;   // channels staged in shared memory per chunk
-
-__device__ __forceinline__ uint32_t orderable(float s) {
-  uint32_t u = __float_as_uint(s);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ uint64_t make_key(float s, int j) {
-  return ((uint64_t)orderable(s) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)j);
-}
-__device__ __forceinline__ float key_score(uint64_t key) {
-  uint32_t u = (uint32_t)(key >> 32);
-  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
-  return __uint_as_float(u);
-}
-
-// Min-heap of `n` keys at h[0], h[NT], h[2*NT], ... : place `key` starting from the
-// root and sift it down.  The root is the worst of the kept candidates.
-__device__ __forceinline__ void sift_from_root(uint64_t* h, int n, uint64_t key) {
-  int p = 0;
-  while (true) {
-    int c = 2 * p + 1;
-    if (c >= n) break;
-    uint64_t kc = h[c * NT];
-    if (c + 1 < n) {
-      uint64_t k2 = h[(c + 1) * NT];
-      if (k2 < kc) { kc = k2; c = c + 1; }
-    }
-    if (kc >= key) break;
-    h[p * NT] = kc;
-    p = c;
-  }
-  h[p * NT] = key;
-}
+constexpr int OFFER = 8;      // candidates offered between overflow checks
+constexpr int CAP = 2 * OFFER;
+using Selector = ecb200::topk::RowSelector<NT, CAP>;
 
 __global__ void __launch_bounds__(NT)
 knn_fma_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int k,
                int KC, int32_t* __restrict__ idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* heap = reinterpret_cast<uint64_t*>(smem_raw);  // [k][NT]
-  float* Qs = reinterpret_cast<float*>(heap + (size_t)k * NT);  // [KC][R]   query rows, c-major
-  float* Cs = Qs + KC * R;                                  // [KC][TJ]  candidate tile, c-major
-  float* hx = Cs + KC * TJ;                                 // [TJ]      -0.5*|xj|^2
+  float* Qs = reinterpret_cast<float*>(smem_raw + Selector::smem_bytes(k));  // [KC][R]  c-major
+  float* Cs = Qs + KC * R;                                                   // [KC][TJ] c-major
+  float* hx = Cs + KC * TJ;                                                  // [TJ] -0.5*|xj|^2
 
   const int b = blockIdx.y;
   const int row0 = blockIdx.x * R;
@@ -69,11 +40,8 @@ knn_fma_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C,
   const int h = tid / R;  // warp-uniform: which half of each candidate tile
   const float* xb = x + (size_t)b * C * N;
   const float* xxb = xx + (size_t)b * N;
-  uint64_t* my = heap + tid;
-
-  for (int p = 0; p < k; ++p) my[p * NT] = 0ull;
-  uint64_t thr_key = 0ull;
-  float thr_s = -CUDART_INF_F;
+  Selector sel;
+  sel.init(smem_raw, k, tid);
   const int nchunks = (C + KC - 1) / KC;
 
   for (int j0 = 0; j0 < N; j0 += TJ) {
@@ -112,45 +80,32 @@ knn_fma_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C,
         }
       }
     }
-    // selection: candidates arrive in ascending j, so ">=" on the score followed by
-    // the exact key compare keeps the (score, smaller-j) total order.
+    // selection: out-of-range candidates carry -inf and can only pass while the heap still
+    // has empty slots, so they are masked explicitly
     const int jbase = j0 + h * HALF;
 #pragma unroll
-    for (int u = 0; u < HALF; ++u) {
-      const float s = acc[u];
-      if (jbase + u < N && s >= thr_s) {
-        const uint64_t key = make_key(s, jbase + u);
-        if (key > thr_key) {
-          sift_from_root(my, k, key);
-          thr_key = my[0];
-          thr_s = key_score(thr_key);
-        }
+    for (int g = 0; g < HALF / OFFER; ++g) {
+#pragma unroll
+      for (int u = 0; u < OFFER; ++u) {
+        const int j = jbase + g * OFFER + u;
+        if (j < N) sel.offer(acc[g * OFFER + u], j);
       }
+      sel.maybe_flush(CAP - OFFER);
     }
   }
+  sel.flush();
 
   // merge the two halves of each row into the h == 0 thread's heap
   __syncthreads();
   if (h == 0) {
-    const uint64_t* other = heap + tid + R;
-    for (int p = 0; p < k; ++p) {
-      const uint64_t key = other[p * NT];
-      if (key > thr_key) {
-        sift_from_root(my, k, key);
-        thr_key = my[0];
-      }
-    }
-    // heap sort in place: afterwards my[0..k-1] is descending (nearest first)
-    for (int n = k - 1; n > 0; --n) {
-      const uint64_t last = my[n * NT];
-      my[n * NT] = my[0];
-      sift_from_root(my, n, last);
-    }
+    const uint64_t* other = sel.heap + R;
+    for (int p = 0; p < k; ++p) sel.insert_key(other[p * NT]);
+    sel.sort_descending();
     const int row = row0 + r;
     if (row < N) {
       int32_t* out = idx + ((size_t)b * N + row) * k;
       for (int p = 0; p < k; ++p) {
-        uint32_t j = 0xFFFFFFFFu - (uint32_t)(my[p * NT] & 0xFFFFFFFFull);
+        const uint32_t j = ecb200::topk::key_index(sel.heap[p * NT]);
         out[p] = (int32_t)min(j, (uint32_t)(N - 1));  // only NaN input can leave an empty slot
       }
     }
@@ -193,11 +148,11 @@ extern "C" int ecb200_knn(const float* x, const float* xx, int B, int C, int N, 
   ECB_REQUIRE(k >= 1 && k <= N, "ecb200_knn: k=%d out of range for N=%d (selected index k out of range)", k, N);
   ECB_REQUIRE(k <= ECB200_MAX_K, "ecb200_knn: k=%d exceeds ECB200_MAX_K=%d", k, ECB200_MAX_K);
   const int KC = C < KC_MAX ? C : KC_MAX;
-  const size_t smem = (size_t)k * NT * sizeof(uint64_t) + (size_t)KC * (R + TJ) * sizeof(float) +
+  const size_t smem = Selector::smem_bytes(k) + (size_t)KC * (R + TJ) * sizeof(float) +
                       TJ * sizeof(float);
   static thread_local bool seen[ecb200::kMaxDevices] = {};
   if (ecb200::first_use_on_device(seen)) {
-    const size_t smem_max = (size_t)ECB200_MAX_K * NT * sizeof(uint64_t) +
+    const size_t smem_max = Selector::smem_bytes(ECB200_MAX_K) +
                             (size_t)KC_MAX * (R + TJ) * sizeof(float) + TJ * sizeof(float);
     ECB_CUDA(cudaFuncSetAttribute(knn_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_max));

@@ -263,26 +263,51 @@ def test_dgcnn_golden_eval(ec):
 def test_dgcnn_config1_shape_vs_oracle_on_same_graphs(ec):
     """BASELINE config 1 shapes (N=1024, k=20, emb 1024) on a batch the CPU oracle
     finishes in seconds; the oracle is driven with OUR per-layer graphs so the EdgeConv
-    arithmetic is compared exactly, and the graphs are compared separately."""
+    arithmetic is compared exactly, and the graphs are compared separately.
+
+    The loss is a fixed random projection of the output.  (A loss like mean(y^2) makes the
+    gradient entering conv5's BatchNorm almost parallel to the normalised activations;
+    cuDNN's fp32 BatchNorm backward -- torch code outside this path -- then loses ~1e-4
+    to cancellation, which tools/diag_precision.py shows is not an EdgeConv error.)
+    Each quantity is also judged against the fp64 oracle."""
     torch.manual_seed(5)
     args = SimpleNamespace(emb_dim=1024, k=20)
     net = ec.DGCNN(args).to(dev()).train()
     net.record_idx = True
-    ref = orc.DGCNNOracle(args)
-    ref.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
-    ref.train()
-    x = orc.synthetic_xyz(4, 1024, seed=1)
+    sd = {k: v.cpu() for k, v in net.state_dict().items()}
+    x = orc.synthetic_xyz(2, 1024, seed=1)
     xg = x.to(dev()).requires_grad_(True)
     y = net(xg)
-    y.square().mean().backward()
+    gout = torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
+    (y * gout.to(dev())).sum().backward()
     idx_list = [i.long().cpu() for i in net.last_idx]
-    xr = x.clone().requires_grad_(True)
-    yr = ref(xr, idx_list=idx_list)
-    yr.square().mean().backward()
-    assert_rel(y, yr, what="out")
-    assert_rel(xg.grad, xr.grad, what="dx")
-    for (n1, p1), (n2, p2) in zip(net.named_parameters(), ref.named_parameters()):
-        assert_rel(p1.grad, p2.grad, rel=2e-4 if n1.startswith("conv5") else REL, what=f"grad {n1}")
+
+    def run_oracle(dtype):
+        ref = orc.DGCNNOracle(args).to(dtype)
+        ref.load_state_dict(sd)
+        ref.train()
+        xr = x.detach().clone().to(dtype).requires_grad_(True)
+        yr = ref(xr, idx_list=idx_list)
+        (yr * gout.to(dtype)).sum().backward()
+        return yr.detach(), xr.grad, {n: p.grad for n, p in ref.named_parameters()}
+
+    y32, dx32, g32 = run_oracle(torch.float32)
+    y64, dx64, g64 = run_oracle(torch.float64)
+
+    def judge(ours, r32, r64, what):
+        ours, r32 = ours.detach().cpu().double(), r32.double()
+        scale = r64.abs().max().item()
+        e_ours = (ours - r64).abs().max().item()
+        e_ref = (r32 - r64).abs().max().item()
+        d = (ours - r32).abs().max().item()
+        ok = d <= REL * scale or e_ours <= max(REL * scale, 2.0 * e_ref)
+        assert ok, (f"{what}: |ours-ref32| {d:.3e}, |ours-ref64| {e_ours:.3e}, "
+                    f"|ref32-ref64| {e_ref:.3e}, scale {scale:.3e}")
+
+    judge(y, y32, y64, "out")
+    judge(xg.grad, dx32, dx64, "dx")
+    for n, p in net.named_parameters():
+        judge(p.grad, g32[n], g64[n], f"grad {n}")
     # layer-1 graph against the oracle's own kNN on the same input
     rep = orc.knn_mismatch_report(x, idx_list[0], orc.knn_oracle(x, 20), rel_eps=TIE_EPS)
     assert rep["bad_rows"] == 0, rep
