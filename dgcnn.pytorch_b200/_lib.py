@@ -8,19 +8,20 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_double, c_float, c_int, c_void_p
+from ctypes import c_double, c_float, c_int, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libedgeconv_b200.so")
 
-P, I, F, D = c_void_p, c_int, c_float, c_double
+P, I, F, D, Z = c_void_p, c_int, c_float, c_double, c_size_t
 
 # name -> argument types, in the order of include/edgeconv_b200.h (all return int)
 SIGNATURES = {
     "ecb200_sqnorms": (P, I, I, I, P, P),
-    "ecb200_knn": (P, P, I, I, I, I, P, P),
+    "ecb200_knn": (P, P, I, I, I, I, I, P, P),
     "ecb200_split_tf32": (P, I, I, I, P, P, P, P),
-    "ecb200_knn_tc": (P, P, P, I, I, I, I, P, P),
+    "ecb200_knn_tc": (P, P, P, I, I, I, I, I, P, P, Z, P),
+    "ecb200_debug_tc_scores": (P, P, P, I, I, I, P, P),
     "ecb200_graph_feature": (P, P, I, I, I, I, I, P, P),
     "ecb200_graph_feature_bwd": (P, P, I, I, I, I, I, P, P),
     "ecb200_pack_weight": (P, I, I, I, P, P),
@@ -42,6 +43,9 @@ SIGNATURES = {
 # kernels each entry point enqueues (memsets are not counted)
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
 KERNELS_PER_CALL["ecb200_reverse_graph"] = 3
+
+# entry points that do not return an error code
+PLAIN = {"ecb200_version": 0, "ecb200_last_error": 0, "ecb200_knn_tc_workspace_bytes": 3}
 
 _lib = None
 launch_count = 0          # kernels of this library enqueued so far (bench.py's gpu_launches)
@@ -70,6 +74,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.argtypes = list(argtypes)
         fn.restype = c_int
+    lib.ecb200_knn_tc_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.ecb200_knn_tc_workspace_bytes.restype = c_size_t
     lib.ecb200_version.argtypes = []
     lib.ecb200_version.restype = c_int
     lib.ecb200_last_error.argtypes = []

@@ -1,7 +1,7 @@
 // kNN graph by FP32-FMA distance tiles feeding an on-chip top-k selector.
 // Replaces knn() of /root/reference/models/dgcnn.py:6-12: the [B,N,N] matrix of
 // -|xi|^2 + 2 xi.xj - |xj|^2 is produced tile by tile in registers and consumed
-// immediately by the per-row top-k selector of topk_select.cuh; only idx[B,N,k] reaches HBM.
+// immediately by the two-pass top-k selector of topk_select.cuh; only idx[B,N,k] reaches HBM.
 //
 // Ranking key.  For a fixed query i the reference's score differs from
 //   s_ij = xi.xj - 0.5*|xj|^2
@@ -16,22 +16,75 @@
 
 namespace {
 
+using namespace ecb200::topk;
+
 constexpr int R = 64;         // query rows per CTA
 constexpr int TJ = 64;        // candidates per tile
 constexpr int NT = 128;       // threads per CTA: two per row, one per half of each tile
-constexpr int HALF = TJ / 2;  // candidates a thread scores per tile
+constexpr int HALF = TJ / 2;  // candidates a thread scores per tile (== NB register bins)
 constexpr int KC_MAX = 128;   // channels staged in shared memory per chunk
 constexpr int OFFER = 8;      // candidates offered between overflow checks
-constexpr int CAP = 2 * OFFER;
-using Selector = ecb200::topk::RowSelector<NT, CAP>;
+constexpr int CAP_MIN = 48;   // survivor slots per thread (expected use: ~12 at k=20, ~24 at k=40)
+static_assert(HALF == NB, "one register bin per candidate slot of a tile");
+using Surv = Survivors<NT>;
+
+struct Tiles {
+  float* Qs;  // [KC][R]   query rows, c-major
+  float* Cs;  // [KC][TJ]  candidate tile, c-major
+  float* hx;  // [TJ]      -0.5*|xj|^2, -inf past the end of the cloud
+};
+
+// scores of this thread's 32 candidates of tile j0:  acc[u] = xi.xj - 0.5*|xj|^2
+__device__ __forceinline__ void score_tile(const float* __restrict__ xb, const float* __restrict__ xxb,
+                                           int C, int N, int KC, int j0, int row0, int tid, int r,
+                                           int h, const Tiles& t, float (&acc)[HALF]) {
+  const int nchunks = (C + KC - 1) / KC;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int c0 = ch * KC;
+    const int kc = min(KC, C - c0);
+    __syncthreads();  // previous tile / chunk fully consumed
+    for (int e = tid; e < kc * TJ; e += NT) {
+      int c = e / TJ, jj = e % TJ;
+      t.Cs[e] = (j0 + jj < N) ? xb[(size_t)(c0 + c) * N + j0 + jj] : 0.f;
+    }
+    if (nchunks > 1 || j0 == 0) {
+      for (int e = tid; e < kc * R; e += NT) {
+        int c = e / R, rr = e % R;
+        t.Qs[e] = (row0 + rr < N) ? xb[(size_t)(c0 + c) * N + row0 + rr] : 0.f;
+      }
+    }
+    if (ch == 0 && tid < TJ) t.hx[tid] = (j0 + tid < N) ? -0.5f * xxb[j0 + tid] : -CUDART_INF_F;
+    __syncthreads();
+    if (ch == 0) {
+#pragma unroll
+      for (int u = 0; u < HALF; ++u) acc[u] = t.hx[h * HALF + u];
+    }
+#pragma unroll 2
+    for (int c = 0; c < kc; ++c) {
+      const float q = t.Qs[c * R + r];
+      const float4* cp = reinterpret_cast<const float4*>(t.Cs + c * TJ + h * HALF);
+#pragma unroll
+      for (int v = 0; v < HALF / 4; ++v) {
+        float4 w = cp[v];  // same address in every lane: broadcast
+        acc[4 * v + 0] = fmaf(q, w.x, acc[4 * v + 0]);
+        acc[4 * v + 1] = fmaf(q, w.y, acc[4 * v + 1]);
+        acc[4 * v + 2] = fmaf(q, w.z, acc[4 * v + 2]);
+        acc[4 * v + 3] = fmaf(q, w.w, acc[4 * v + 3]);
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(NT)
 knn_fma_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C, int N, int k,
-               int KC, int32_t* __restrict__ idx) {
+               int KC, int cap, int sorted, int32_t* __restrict__ idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* Qs = reinterpret_cast<float*>(smem_raw + Selector::smem_bytes(k));  // [KC][R]  c-major
-  float* Cs = Qs + KC * R;                                                   // [KC][TJ] c-major
-  float* hx = Cs + KC * TJ;                                                  // [TJ] -0.5*|xj|^2
+  float* sbin = reinterpret_cast<float*>(smem_raw + Surv::smem_bytes(cap));  // [NB][NT] sorted bin maxima
+  int* scnt = reinterpret_cast<int*>(sbin + NB * NT);                      // [NT] survivor counts
+  Tiles t;
+  t.Qs = reinterpret_cast<float*>(scnt + NT);
+  t.Cs = t.Qs + KC * R;
+  t.hx = t.Cs + KC * TJ;
 
   const int b = blockIdx.y;
   const int row0 = blockIdx.x * R;
@@ -40,75 +93,150 @@ knn_fma_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C,
   const int h = tid / R;  // warp-uniform: which half of each candidate tile
   const float* xb = x + (size_t)b * C * N;
   const float* xxb = xx + (size_t)b * N;
-  Selector sel;
-  sel.init(smem_raw, k, tid);
-  const int nchunks = (C + KC - 1) / KC;
+  float acc[HALF];
 
+  // ---- pass A: bin maxima -> per-row threshold
+  float bin[NB];
+#pragma unroll
+  for (int u = 0; u < NB; ++u) bin[u] = -CUDART_INF_F;
   for (int j0 = 0; j0 < N; j0 += TJ) {
-    float acc[HALF];
-    for (int ch = 0; ch < nchunks; ++ch) {
-      const int c0 = ch * KC;
-      const int kc = min(KC, C - c0);
-      __syncthreads();  // previous tile / chunk fully consumed
-      for (int e = tid; e < kc * TJ; e += NT) {
-        int c = e / TJ, jj = e % TJ;
-        Cs[e] = (j0 + jj < N) ? xb[(size_t)(c0 + c) * N + j0 + jj] : 0.f;
-      }
-      if (nchunks > 1 || j0 == 0) {
-        for (int e = tid; e < kc * R; e += NT) {
-          int c = e / R, rr = e % R;
-          Qs[e] = (row0 + rr < N) ? xb[(size_t)(c0 + c) * N + row0 + rr] : 0.f;
-        }
-      }
-      if (ch == 0 && tid < TJ) hx[tid] = (j0 + tid < N) ? -0.5f * xxb[j0 + tid] : -CUDART_INF_F;
-      __syncthreads();
-      if (ch == 0) {
+    score_tile(xb, xxb, C, N, KC, j0, row0, tid, r, h, t, acc);
 #pragma unroll
-        for (int u = 0; u < HALF; ++u) acc[u] = hx[h * HALF + u];
-      }
-#pragma unroll 2
-      for (int c = 0; c < kc; ++c) {
-        const float q = Qs[c * R + r];
-        const float4* cp = reinterpret_cast<const float4*>(Cs + c * TJ + h * HALF);
+    for (int u = 0; u < NB; ++u) bin[u] = fmaxf(bin[u], acc[u]);
+  }
+  sort32_desc(bin);
 #pragma unroll
-        for (int v = 0; v < HALF / 4; ++v) {
-          float4 t = cp[v];  // same address in every lane: broadcast
-          acc[4 * v + 0] = fmaf(q, t.x, acc[4 * v + 0]);
-          acc[4 * v + 1] = fmaf(q, t.y, acc[4 * v + 1]);
-          acc[4 * v + 2] = fmaf(q, t.z, acc[4 * v + 2]);
-          acc[4 * v + 3] = fmaf(q, t.w, acc[4 * v + 3]);
-        }
-      }
-    }
-    // selection: out-of-range candidates carry -inf and can only pass while the heap still
-    // has empty slots, so they are masked explicitly
+  for (int u = 0; u < NB; ++u) sbin[u * NT + tid] = bin[u];
+  __syncthreads();
+  // both threads of a row derive the same tau from the row's 64 bins
+  const float tau = fmaxf(kth_of_sorted_columns<2>(sbin, r, R, NT, k), -3.0e38f);
+
+  // ---- pass B: keep the candidates that reach tau
+  Surv sv;
+  sv.init(smem_raw, tid, cap, tau);
+  for (int j0 = 0; j0 < N; j0 += TJ) {
+    score_tile(xb, xxb, C, N, KC, j0, row0, tid, r, h, t, acc);
     const int jbase = j0 + h * HALF;
 #pragma unroll
     for (int g = 0; g < HALF / OFFER; ++g) {
+      sv.guard(k, OFFER);
 #pragma unroll
       for (int u = 0; u < OFFER; ++u) {
         const int j = jbase + g * OFFER + u;
-        if (j < N) sel.offer(acc[g * OFFER + u], j);
+        if (j < N) sv.offer(acc[g * OFFER + u], j);
       }
-      sel.maybe_flush(CAP - OFFER);
     }
   }
-  sel.flush();
-
-  // merge the two halves of each row into the h == 0 thread's heap
+  scnt[tid] = sv.cnt;
   __syncthreads();
-  if (h == 0) {
-    const uint64_t* other = sel.heap + R;
-    for (int p = 0; p < k; ++p) sel.insert_key(other[p * NT]);
-    sel.sort_descending();
-    const int row = row0 + r;
-    if (row < N) {
-      int32_t* out = idx + ((size_t)b * N + row) * k;
-      for (int p = 0; p < k; ++p) {
-        const uint32_t j = ecb200::topk::key_index(sel.heap[p * NT]);
-        out[p] = (int32_t)min(j, (uint32_t)(N - 1));  // only NaN input can leave an empty slot
+
+  // ---- exact top-k: both threads of a row rank their own survivors against the union
+  if (row0 + r < N) {
+    const int cnts[2] = {scnt[r], scnt[r + R]};
+    int32_t* out = idx + ((size_t)b * N + row0 + r) * k;
+    // fewer than k survivors only if the input held NaNs: keep every slot in range
+    if (h == 0 && cnts[0] + cnts[1] < k)
+      for (int p = cnts[0] + cnts[1]; p < k; ++p) out[p] = N - 1;
+    rank_and_write<NT, 2>(reinterpret_cast<const uint64_t*>(smem_raw), r, R, cnts, h, k, N - 1, out);
+  }
+}
+
+// ---- xyz specialisation (C <= 3): the whole cloud sits in shared memory as packed
+// (x, y, z, -0.5*|p|^2); a row's coordinates live in registers; 4 threads share a row,
+// each scanning every fourth group of 32 candidates.  ~5 instructions per pair and pass.
+constexpr int XR = 32;        // rows per CTA
+constexpr int XT = 4;         // threads per row
+constexpr int XNT = XR * XT;  // 128 threads
+constexpr int XCAP_MIN = 32;  // survivor slots per thread (expected use: ~6 at k=20, ~12 at k=40)
+constexpr int XTILE = 4096;   // candidates staged at a time (64 KB)
+using XSurv = Survivors<XNT>;
+
+template <int C>
+__global__ void __launch_bounds__(XNT)
+knn_xyz_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int k, int cap,
+               int sorted, int32_t* __restrict__ idx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sbin = reinterpret_cast<float*>(smem_raw + XSurv::smem_bytes(cap));  // [NB][XNT]
+  int* scnt = reinterpret_cast<int*>(sbin + NB * XNT);                      // [XNT]
+  float4* cand = reinterpret_cast<float4*>(scnt + XNT);                     // [<= XTILE]
+
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * XR;
+  const int tid = threadIdx.x;
+  const int r = tid % XR;
+  const int h = tid / XR;  // warp index: which group of 32 within each 128 candidates
+  const float* xb = x + (size_t)b * C * N;
+  const float* xxb = xx + (size_t)b * N;
+  const int row = min(row0 + r, N - 1);
+  const float q0 = xb[row];
+  const float q1 = C > 1 ? xb[(size_t)N + row] : 0.f;
+  const float q2 = C > 2 ? xb[2 * (size_t)N + row] : 0.f;
+
+  auto stage = [&](int t0, int tn) {  // candidates [t0, t0+tn) -> smem, padded to 128 with -inf
+    __syncthreads();
+    const int padded = (tn + XNT - 1) / XNT * XNT;
+    for (int e = tid; e < padded; e += XNT) {
+      float4 c = make_float4(0.f, 0.f, 0.f, -CUDART_INF_F);
+      if (e < tn) {
+        const int j = t0 + e;
+        c.x = xb[j];
+        if (C > 1) c.y = xb[(size_t)N + j];
+        if (C > 2) c.z = xb[2 * (size_t)N + j];
+        c.w = -0.5f * xxb[j];
+      }
+      cand[e] = c;
+    }
+    __syncthreads();
+    return padded;
+  };
+  auto score = [&](const float4& c) { return fmaf(q0, c.x, fmaf(q1, c.y, fmaf(q2, c.z, c.w))); };
+
+  // ---- pass A: bin maxima -> threshold
+  float bin[NB];
+#pragma unroll
+  for (int u = 0; u < NB; ++u) bin[u] = -CUDART_INF_F;
+  for (int t0 = 0; t0 < N; t0 += XTILE) {
+    const int padded = stage(t0, min(XTILE, N - t0));
+    for (int j0 = h * NB; j0 < padded; j0 += XNT) {
+#pragma unroll
+      for (int u = 0; u < NB; ++u) bin[u] = fmaxf(bin[u], score(cand[j0 + u]));
+    }
+  }
+  sort32_desc(bin);
+#pragma unroll
+  for (int u = 0; u < NB; ++u) sbin[u * XNT + tid] = bin[u];
+  __syncthreads();
+  // -3e38 floor: padding candidates score -inf and must never pass, even when the cloud has
+  // fewer than k non-empty bins
+  const float tau = fmaxf(kth_of_sorted_columns<XT>(sbin, r, XR, XNT, k), -3.0e38f);
+
+  // ---- pass B: survivors
+  XSurv sv;
+  sv.init(smem_raw, tid, cap, tau);
+  for (int t0 = 0; t0 < N; t0 += XTILE) {
+    const int padded = (N <= XTILE) ? (N + XNT - 1) / XNT * XNT : stage(t0, min(XTILE, N - t0));
+    for (int j0 = h * NB; j0 < padded; j0 += XNT) {
+#pragma unroll
+      for (int g = 0; g < NB / 8; ++g) {
+        sv.guard(k, 8);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sv.offer(score(cand[j0 + g * 8 + u]), t0 + j0 + g * 8 + u);
       }
     }
+  }
+  scnt[tid] = sv.cnt;
+  __syncthreads();
+
+  // ---- exact top-k: the four threads of a row rank their own survivors against the union
+  if (row0 + r < N) {
+    int cnts[XT];
+    int m = 0;
+#pragma unroll
+    for (int t = 0; t < XT; ++t) { cnts[t] = scnt[r + t * XR]; m += cnts[t]; }
+    int32_t* out = idx + ((size_t)b * N + row0 + r) * k;
+    if (h == 0 && m < k)  // only with NaN input
+      for (int p = m; p < k; ++p) out[p] = N - 1;
+    rank_and_write<XNT, XT>(reinterpret_cast<const uint64_t*>(smem_raw), r, XR, cnts, h, k, N - 1, out);
   }
 }
 
@@ -139,7 +267,7 @@ extern "C" int ecb200_sqnorms(const float* x, int B, int C, int N, float* xx, vo
   return ECB200_OK;
 }
 
-extern "C" int ecb200_knn(const float* x, const float* xx, int B, int C, int N, int k,
+extern "C" int ecb200_knn(const float* x, const float* xx, int B, int C, int N, int k, int sorted,
                           int32_t* idx, void* stream) {
   ECB_REQUIRE(x && xx && idx, "ecb200_knn: null pointer");
   ECB_REQUIRE(B >= 1 && C >= 1 && N >= 1, "ecb200_knn: bad shape B=%d C=%d N=%d", B, C, N);
@@ -147,18 +275,42 @@ extern "C" int ecb200_knn(const float* x, const float* xx, int B, int C, int N, 
   // same trigger as Tensor.topk in the reference (dgcnn.py:11): k must not exceed N
   ECB_REQUIRE(k >= 1 && k <= N, "ecb200_knn: k=%d out of range for N=%d (selected index k out of range)", k, N);
   ECB_REQUIRE(k <= ECB200_MAX_K, "ecb200_knn: k=%d exceeds ECB200_MAX_K=%d", k, ECB200_MAX_K);
+  if (C <= 3) {
+    const int staged = N < XTILE ? (N + XNT - 1) / XNT * XNT : XTILE;
+    const int cap = XSurv::capacity(k, 8, XCAP_MIN);
+    const size_t smem = XSurv::smem_bytes(cap) + (size_t)NB * XNT * sizeof(float) + XNT * sizeof(int) +
+                        (size_t)staged * sizeof(float4);
+    const size_t smem_max = XSurv::smem_bytes(XSurv::capacity(ECB200_MAX_K, 8, XCAP_MIN)) +
+                            (size_t)NB * XNT * sizeof(float) + XNT * sizeof(int) +
+                            (size_t)XTILE * sizeof(float4);
+    static thread_local bool seen_xyz[ecb200::kMaxDevices] = {};
+    if (ecb200::first_use_on_device(seen_xyz)) {
+      ECB_CUDA(cudaFuncSetAttribute(knn_xyz_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+      ECB_CUDA(cudaFuncSetAttribute(knn_xyz_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+      ECB_CUDA(cudaFuncSetAttribute(knn_xyz_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    }
+    dim3 grid(ecb200::ceil_div(N, XR), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 1) knn_xyz_kernel<1><<<grid, XNT, smem, st>>>(x, xx, N, k, cap, sorted, idx);
+    else if (C == 2) knn_xyz_kernel<2><<<grid, XNT, smem, st>>>(x, xx, N, k, cap, sorted, idx);
+    else knn_xyz_kernel<3><<<grid, XNT, smem, st>>>(x, xx, N, k, cap, sorted, idx);
+    ECB_LAUNCH_CHECK("knn_xyz_kernel");
+    return ECB200_OK;
+  }
   const int KC = C < KC_MAX ? C : KC_MAX;
-  const size_t smem = Selector::smem_bytes(k) + (size_t)KC * (R + TJ) * sizeof(float) +
+  const int cap = Surv::capacity(k, OFFER, CAP_MIN);
+  const size_t misc = (size_t)NB * NT * sizeof(float) + NT * sizeof(int);
+  const size_t smem = Surv::smem_bytes(cap) + misc + (size_t)KC * (R + TJ) * sizeof(float) +
                       TJ * sizeof(float);
   static thread_local bool seen[ecb200::kMaxDevices] = {};
   if (ecb200::first_use_on_device(seen)) {
-    const size_t smem_max = Selector::smem_bytes(ECB200_MAX_K) +
+    const size_t smem_max = Surv::smem_bytes(Surv::capacity(ECB200_MAX_K, OFFER, CAP_MIN)) + misc +
                             (size_t)KC_MAX * (R + TJ) * sizeof(float) + TJ * sizeof(float);
     ECB_CUDA(cudaFuncSetAttribute(knn_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_max));
   }
   dim3 grid(ecb200::ceil_div(N, R), B);
-  knn_fma_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(x, xx, C, N, k, KC, idx);
+  knn_fma_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(x, xx, C, N, k, KC, cap, sorted, idx);
   ECB_LAUNCH_CHECK("knn_fma_kernel");
   return ECB200_OK;
 }

@@ -79,7 +79,7 @@ def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
         raise RuntimeError("edgeconv_block expects a bias-free 1x1 Conv2d")
     x = _as_f32(x)
     if idx is None:
-        idx = ops.knn_op(x.detach().contiguous(), int(k))
+        idx = ops.knn_op(x.detach().contiguous(), int(k), False)   # order over k is irrelevant here
     group = 0
     if isinstance(bn, nn.SyncBatchNorm) and bn.training and torch.distributed.is_available() \
             and torch.distributed.is_initialized():

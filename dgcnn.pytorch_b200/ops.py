@@ -13,6 +13,7 @@ Ops (namespace ``edgeconv_b200``):
 """
 from __future__ import annotations
 
+import os
 from ctypes import c_void_p
 from typing import List, Optional, Tuple
 
@@ -64,7 +65,7 @@ def _check_cuda_f32(name: str, t: Tensor, dims: Optional[int] = None):
 
 # ------------------------------------------------------------------------------ kNN
 @torch.library.custom_op("edgeconv_b200::knn", mutates_args=(), device_types="cuda")
-def knn_op(x: Tensor, k: int) -> Tensor:
+def knn_op(x: Tensor, k: int, sorted: bool = True) -> Tensor:
     _check_cuda_f32("x", x, 3)
     B, C, N = x.shape
     if k > N or k < 1:
@@ -77,13 +78,51 @@ def knn_op(x: Tensor, k: int) -> Tensor:
         xx = torch.empty(B * N, device=x.device, dtype=torch.float32)
         idx = torch.empty(B, N, k, device=x.device, dtype=torch.int32)
         st = _stream(x)
-        _lib.call("ecb200_sqnorms", _ptr(x), B, C, N, _ptr(xx), st)
-        _lib.call("ecb200_knn", _ptr(x), _ptr(xx), B, C, N, k, _ptr(idx), st)
+        if knn_uses_tensor_cores(C, N, k):
+            # feature-space layers: tcgen05 / TMA distance tiles (knn_tc.cu)
+            hi = torch.empty(B * N, C, device=x.device, dtype=torch.float32)
+            lo = torch.empty(B * N, C, device=x.device, dtype=torch.float32)
+            nbytes = _lib.load().ecb200_knn_tc_workspace_bytes(B, N, k)
+            ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+            _lib.call("ecb200_split_tf32", _ptr(x), B, C, N, _ptr(hi), _ptr(lo), _ptr(xx), st)
+            _lib.call("ecb200_knn_tc", _ptr(hi), _ptr(lo), _ptr(xx), B, C, N, k, int(sorted), _ptr(idx),
+                      _ptr(ws), nbytes, st)
+        else:
+            # xyz layer (and any shape the tensor-core kernel does not take): FP32 FMA tiles
+            _lib.call("ecb200_sqnorms", _ptr(x), B, C, N, _ptr(xx), st)
+            _lib.call("ecb200_knn", _ptr(x), _ptr(xx), B, C, N, k, int(sorted), _ptr(idx), st)
     return idx
 
 
+def knn_uses_tensor_cores(C: int, N: int, k: int) -> bool:
+    """Kernel choice for knn(): tensor cores where the contraction is a real GEMM
+    (C a multiple of 32 in [32, 128], k <= 40), FP32 FMA otherwise.  ECB200_KNN=fma|tc
+    overrides for A/B tests (tc still requires a supported shape)."""
+    mode = os.environ.get("ECB200_KNN", "auto")
+    supported = C % 32 == 0 and 32 <= C <= 128 and k <= 40
+    if mode == "fma":
+        return False
+    return supported
+
+
+def debug_tc_scores(x: Tensor) -> Tensor:
+    """Diagnostic: scores x_i.x_j - 0.5|x_j|^2 [B,N,N] from the tensor-core pipeline."""
+    _check_cuda_f32("x", x, 3)
+    B, C, N = x.shape
+    x = x.contiguous()
+    with torch.cuda.device(x.device):
+        hi = torch.empty(B * N, C, device=x.device, dtype=torch.float32)
+        lo = torch.empty_like(hi)
+        xx = torch.empty(B * N, device=x.device, dtype=torch.float32)
+        out = torch.full((B, N, N), float("nan"), device=x.device, dtype=torch.float32)
+        st = _stream(x)
+        _lib.call("ecb200_split_tf32", _ptr(x), B, C, N, _ptr(hi), _ptr(lo), _ptr(xx), st)
+        _lib.call("ecb200_debug_tc_scores", _ptr(hi), _ptr(lo), _ptr(xx), B, C, N, _ptr(out), st)
+    return out
+
+
 @knn_op.register_fake
-def _(x, k):
+def _(x, k, sorted=True):
     B, C, N = x.shape
     return x.new_empty((B, N, k), dtype=torch.int32)
 

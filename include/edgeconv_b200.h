@@ -69,21 +69,31 @@ const char* ecb200_last_error(void);
 int ecb200_sqnorms(const float* x, int B, int C, int N, float* xx, void* stream);
 
 /* idx[b,i,0..k-1] = the k points j of cloud b with the largest
- * -|x_i|^2 + 2 x_i.x_j - |x_j|^2 (dgcnn.py:9-11), nearest first; ties broken
- * towards the smaller j.  FP32 FMA distance tiles feeding an on-chip top-k
- * selector: the [B,N,N] matrix is never written.  Requires 1 <= k <= min(N, 64). */
-int ecb200_knn(const float* x, const float* xx, int B, int C, int N, int k,
+ * -|x_i|^2 + 2 x_i.x_j - |x_j|^2 (dgcnn.py:9-11); ties broken towards the smaller j.
+ * sorted != 0: nearest first, as Tensor.topk returns them; sorted == 0: the same set in
+ * unspecified order (enough for EdgeConv, whose reductions over k are order-free).
+ * FP32 FMA distance tiles feeding an on-chip top-k selector: the [B,N,N] matrix is never
+ * written.  Requires 1 <= k <= min(N, 64). */
+int ecb200_knn(const float* x, const float* xx, int B, int C, int N, int k, int sorted,
                int32_t* idx, void* stream);
 
-/* Tensor-core variant for feature-space layers (C % 8 == 0, C <= 256): tcgen05
- * kind::tf32 tiles with 3xTF32 error compensation, accumulators in TMEM, same
- * selector.  Needs the point-major hi/lo operands made by ecb200_split_tf32.
- * (declared now so the binding is stable; returns ECB200_ERR_ARG if the build
- * does not carry the kernel) */
+/* Tensor-core variant for the feature-space layers (C a multiple of 32 in [32,128],
+ * k <= 40): tcgen05 kind::tf32 tiles with 3xTF32 error compensation, FP32 accumulators in
+ * TMEM, operand tiles moved by TMA, the same on-chip selector.
+ *   ecb200_split_tf32: x[B,C,N] -> point-major hi = tf32(x), lo = tf32(x - hi) [B*N, C] and
+ *                      xx[B*N] (same values as ecb200_sqnorms)
+ *   ecb200_knn_tc:     idx as ecb200_knn; `workspace` (ecb200_knn_tc_workspace_bytes) holds the
+ *                      per-row survivor lists of the selector's second pass.
+ *   ecb200_debug_tc_scores: diagnostic -- the raw scores x_i.x_j - 0.5|x_j|^2 [B,N,N] produced
+ *                      by the same MMA pipeline (only sensible for small N). */
 int ecb200_split_tf32(const float* x, int B, int C, int N, float* hi, float* lo,
                       float* xx, void* stream);
+size_t ecb200_knn_tc_workspace_bytes(int B, int N, int k);
 int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, int B, int C, int N,
-                  int k, int32_t* idx, void* stream);
+                  int k, int sorted, int32_t* idx, void* workspace, size_t workspace_bytes,
+                  void* stream);
+int ecb200_debug_tc_scores(const float* hi, const float* lo, const float* xx, int B, int C, int N,
+                           float* scores, void* stream);
 
 /* ---- materialised graph feature: replaces get_graph_feature(), dgcnn.py:15-44 ------ */
 int ecb200_graph_feature(const float* x, const int32_t* idx, int B, int C, int N, int k,

@@ -27,7 +27,7 @@ def _declared():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     decls = {}
-    for m in re.finditer(r"\b(?:int|const char\*)\s+(ecb200_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"\b(?:int|size_t|const char\*)\s+(ecb200_\w+)\s*\(([^)]*)\)\s*;", text):
         args = m.group(2).strip()
         decls[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
     return decls
@@ -39,23 +39,24 @@ def test_header_symbols_exported_and_bound(ec):
     lib = ctypes.CDLL(ec._lib.LIB_PATH)
     for name, nargs in decls.items():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
-        if name in ("ecb200_version", "ecb200_last_error"):
+        if name in ec._lib.PLAIN:
+            assert ec._lib.PLAIN[name] == nargs, name
             continue
         assert name in ec._lib.SIGNATURES, f"{name} has no ctypes binding"
         assert len(ec._lib.SIGNATURES[name]) == nargs, name
-    assert set(ec._lib.SIGNATURES) <= set(decls)
+    assert set(ec._lib.SIGNATURES) | set(ec._lib.PLAIN) == set(decls)
 
 
 def test_version_and_error_string(ec):
     assert ec._lib.version() == 100
     # argument validation happens before any CUDA call, so it is testable without a GPU
     with pytest.raises(RuntimeError, match="null pointer"):
-        ec._lib.call("ecb200_knn", None, None, 1, 3, 8, 2, None, None)
+        ec._lib.call("ecb200_knn", None, None, 1, 3, 8, 2, 1, None, None)
     one = ctypes.c_void_p(16)
     with pytest.raises(RuntimeError, match="out of range"):
-        ec._lib.call("ecb200_knn", one, one, 1, 3, 8, 9, one, None)       # k > N, like topk
+        ec._lib.call("ecb200_knn", one, one, 1, 3, 8, 9, 1, one, None)    # k > N, like topk
     with pytest.raises(RuntimeError, match="ECB200_MAX_K"):
-        ec._lib.call("ecb200_knn", one, one, 1, 3, 4096, 65, one, None)
+        ec._lib.call("ecb200_knn", one, one, 1, 3, 4096, 65, 1, one, None)
     with pytest.raises(RuntimeError, match="multiple of 4"):
         ec._lib.call("ecb200_edge_gather", one, one, one, 1, 8, 2, 6, one, one, None, None, None)
 

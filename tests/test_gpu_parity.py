@@ -106,6 +106,10 @@ def test_knn_ties_lattice_and_duplicates(ec):
     # tie rule: equal scores resolve to the smaller index
     idx = ec.knn(torch.zeros(1, 3, 40, device=dev()), 7)
     assert torch.equal(idx[0], torch.arange(7, device=dev()).expand(40, 7))
+    # all-equal clouds overflow every survivor buffer: the slow shrink path must hold the rule
+    for C, N, k in ((3, 700, 40), (3, 5000, 64), (16, 300, 33), (130, 200, 64)):
+        idx = ec.knn(torch.ones(2, C, N, device=dev()), k)
+        assert torch.equal(idx[1], torch.arange(k, device=dev()).expand(N, k)), (C, N, k)
 
 
 def test_knn_errors_match_reference_triggers(ec):
