@@ -22,6 +22,7 @@ SIGNATURES = {
     "ecb200_split_tf32": (P, I, I, I, P, P, P, P),
     "ecb200_knn_tc": (P, P, P, I, I, I, I, I, P, P, Z, P),
     "ecb200_debug_tc_scores": (P, P, P, I, I, I, P, P),
+    "ecb200_debug_tc_timeline": (P, P, P, I, I, I, I, P, P, P, P),
     "ecb200_graph_feature": (P, P, I, I, I, I, I, P, P),
     "ecb200_graph_feature_bwd": (P, P, I, I, I, I, I, P, P),
     "ecb200_pack_weight": (P, I, I, I, P, P),

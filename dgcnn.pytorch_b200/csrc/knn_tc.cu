@@ -7,10 +7,10 @@
 //     shared memory in the canonical K-major SWIZZLE_128B layout;
 //   * D[128 queries x 128 candidates] += Ahi.Bhi^T + Ahi.Blo^T + Alo.Bhi^T  (3xTF32 error
 //     compensation, kind::tf32, FP32 accumulators in TMEM) -- one elected thread issues;
-//   * four epilogue warps read the accumulators with tcgen05.ld (lane = query row), add the
-//     -0.5*|x_j|^2 column term and feed the two-pass selector of topk_select.cuh, so the
-//     distance matrix never leaves the SM.  Accumulators are double-buffered in TMEM so the
-//     next tile's MMAs overlap the selection of the current one.
+//   * two epilogue warpgroups (one per TMEM accumulator stage) read the accumulators with
+//     tcgen05.ld (lane = query row), add the -0.5*|x_j|^2 column term and feed the two-pass
+//     selector of topk_select.cuh, so the distance matrix never leaves the SM; MMAs of the
+//     next tile overlap the selection of the current one.
 // The query tile (A) stays resident in shared memory; candidate tiles (B) stream through a
 // TMA / mbarrier ring.  Pass A and pass B of the selector are two sweeps of the same MMAs.
 #include <cuda.h>
@@ -30,18 +30,22 @@ constexpr int BN = 128;                  // candidates per MMA tile (= TMEM colu
 constexpr int KB = 32;                   // channels per K-block: 32 fp32 = one 128-byte swizzle row
 constexpr int TILE_BYTES = BM * KB * 4;  // 16 KB: one K-block of one operand half
 constexpr int MAX_KB = 4;                // C <= 128 keeps the query tile resident
-constexpr int NUM_EPI = 128;             // 4 epilogue warps
-constexpr int NT = 64 + NUM_EPI;         // + producer warp + MMA warp
+constexpr int NUM_EPI = 128;             // threads per epilogue warpgroup (one per TMEM lane)
+constexpr int NT = 64 + 2 * NUM_EPI;     // producer warp + MMA warp + two epilogue warpgroups
 constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator stages
 constexpr int UMMA_K = 8;                // tf32: 32 bytes of K per instruction
+constexpr int KMAX = 40;                 // largest k this kernel takes
 
 struct SharedTail {  // lives after the operand tiles
-  float hx[2][BN];
+  float hx[2][2][BN];          // [group][ping-pong] -0.5*|x_j|^2 of the current column tile
+  float stage_s[16][2 * NUM_EPI];  // pass B: the 16 scores a thread is currently testing
+  int cnt_x[2][NUM_EPI];           // survivor-count exchange between the two threads of a row
   uint64_t a_full, b_full[4], b_empty[4], t_full[2], t_empty[2];
   uint32_t tmem_slot;
 };
 
-__host__ __device__ constexpr int num_stages(int nkb) { return nkb <= 2 ? 4 : 2; }
+// operand area = (2*nkb + 2*stages) * 16 KB must stay >= 160 KB: the final ranking reuses it
+__host__ __device__ constexpr int num_stages(int nkb) { return nkb == 1 ? 4 : (nkb == 2 ? 3 : 2); }
 __host__ __device__ constexpr size_t smem_bytes(int nkb) {
   return 1024 /* alignment slack */ + (size_t)(2 * nkb + 2 * num_stages(nkb)) * TILE_BYTES +
          sizeof(SharedTail);
@@ -67,15 +71,23 @@ __device__ __forceinline__ void sort_bins_desc(float (&v)[NBINS]) {
   }
 }
 
+// Optional timeline (diagnostics): CTA (0,0) stamps clock64() into tl[role*256 + i]
+#define ECB_STAMP(role, i)                                                                  \
+  do {                                                                                      \
+    if (tl && blockIdx.x == 0 && blockIdx.y == 0 && (i) < 256) tl[(role) * 256 + (i)] = clock64(); \
+  } while (0)
+
 // DEBUG = true: one sweep, raw scores written to dbg[B,N,N] (validation of the MMA plumbing)
 template <int NBINS, bool DEBUG>
 __global__ void __launch_bounds__(NT, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
               const float* __restrict__ xx, int N, int nkb, int k, uint64_t* __restrict__ surv_ws,
-              int cap, int32_t* __restrict__ idx, float* __restrict__ dbg) {
+              float* __restrict__ exch, int cap, int32_t* __restrict__ idx, float* __restrict__ dbg,
+              long long* tl) {
   extern __shared__ unsigned char smem_dyn[];
-  unsigned char* base =
-      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round-trip
+  // would turn every later access into a generic-address load/store)
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int S = num_stages(nkb);
   unsigned char* a_hi = base;                                  // [nkb][16 KB]
   unsigned char* a_lo = a_hi + (size_t)nkb * TILE_BYTES;       // [nkb][16 KB]
@@ -101,6 +113,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = T->tmem_slot;
+  if (threadIdx.x == 0) ECB_STAMP(5, 0);
 
   if (warp == 0) {
     // ===================== TMA producer (one lane) =====================
@@ -116,6 +129,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         for (int ct = 0; ct < nct; ++ct)
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&T->b_empty[stage], phase ^ 1);
+            ECB_STAMP(0, (pass * nct + ct) * nkb + kb);
             unsigned char* dst = b_st + (size_t)stage * 2 * TILE_BYTES;
             mbar_expect_tx(&T->b_full[stage], 2 * TILE_BYTES);
             tma_load_2d(dst, &map_hi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
@@ -134,9 +148,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       int tile = 0;
       for (int pass = 0; pass < npass; ++pass)
         for (int ct = 0; ct < nct; ++ct, ++tile) {
-          const int as = tile & 1;
-          mbar_wait(&T->t_empty[as], ((tile >> 1) & 1) ^ 1);  // epilogue drained this stage
+          const int as = tile & 1;  // stage g is consumed by epilogue warpgroup g
+          mbar_wait(&T->t_empty[as], ((tile >> 1) & 1) ^ 1);  // that group drained this stage
           tc_fence_after();
+          ECB_STAMP(1, 2 * tile);
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&T->b_full[stage], phase);
@@ -158,109 +173,201 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
           mma_commit(&T->t_full[as]);  // accumulator ready for the epilogue
+          ECB_STAMP(1, 2 * tile + 1);
         }
     }
   } else {
     // ===================== epilogue: selection (thread = query row) =====================
+    // Two warpgroups: group g owns the tiles that land in accumulator stage g, so while one
+    // group selects from a tile the other already works on the next one.  A row is
+    // therefore served by two threads (one per group), each with its own bins / survivors.
+    const int g = (warp - 2) >> 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;
+    const int et = (threadIdx.x - 64) & (NUM_EPI - 1);
     const int row = rt * BM + q * 32 + lane;
     const bool valid = row < N;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN);
     float bin[NBINS];
 #pragma unroll
     for (int u = 0; u < NBINS; ++u) bin[u] = -CUDART_INF_F;
-    uint64_t* mybuf = surv_ws ? surv_ws + (size_t)(cloud_row0 + (valid ? row : 0)) * cap : nullptr;
+    // workspace layouts are [tile][slot][group][row-in-tile]: for a fixed slot the 32 lanes of
+    // a warp (consecutive rows) touch consecutive words, so the traffic coalesces
+    const size_t tile_id = (size_t)b * gridDim.x + rt;
+    constexpr int LS = 2 * NUM_EPI;  // stride between a thread's consecutive slots
+    uint64_t* mybuf = surv_ws ? surv_ws + tile_id * (size_t)cap * LS + g * NUM_EPI + et : nullptr;
+    float* stage_s = &T->stage_s[0][g * NUM_EPI + et];
     int cnt = 0;
     float thr = CUDART_INF_F;
-    int tile = 0;
+    int use = 0;  // how many times this group has consumed its accumulator stage
     for (int pass = 0; pass < npass; ++pass) {
       if (pass == 1) {
+        if (et == 0) ECB_STAMP(4, 8 * g + 5);
         sort_bins_desc<NBINS>(bin);
-        float tau = -CUDART_INF_F;
+        if (et == 0) ECB_STAMP(4, 8 * g + 6);
+        float tau;
+        // The row's two threads pool their bins: the k-th largest of the union of both
+        // sorted lists is  max_i min(mine[i-1], theirs[k-i-1])  (i taken from mine).  The
+        // lists travel through the L2-resident workspace (shared memory is full of tiles).
+        float* myx = exch + tile_id * (size_t)KMAX * LS + g * NUM_EPI + et;
+        const float* ox = exch + tile_id * (size_t)KMAX * LS + (g ^ 1) * NUM_EPI + et;
 #pragma unroll
-        for (int u = 0; u < NBINS; ++u)
-          if (u == k - 1) tau = bin[u];
+        for (int u = 0; u < KMAX; ++u)
+          if (u < k) myx[u * LS] = u < NBINS ? bin[u < NBINS ? u : 0] : -CUDART_INF_F;
+        __threadfence_block();
+        asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
+        tau = -CUDART_INF_F;
+        float theirs[KMAX + 1];
+#pragma unroll
+        for (int i = 0; i <= KMAX; ++i) theirs[i] = __ldcg(ox + max(k - i - 1, 0) * LS);  // independent loads
+#pragma unroll
+        for (int i = 0; i <= KMAX; ++i) {
+          const float mine = i == 0 ? CUDART_INF_F : (i - 1 < NBINS ? bin[i - 1 < NBINS ? i - 1 : 0] : -CUDART_INF_F);
+          const float t = i >= k ? CUDART_INF_F : theirs[i];
+          if (i <= k) tau = fmaxf(tau, fminf(mine, t));
+        }
         thr = fmaxf(tau, -3.0e38f);  // masked candidates score -inf and must never pass
+        if (et == 0) ECB_STAMP(4, 8 * g + 7);
       }
-      for (int ct = 0; ct < nct; ++ct, ++tile) {
-        const int as = tile & 1;
+      for (int ct = (pass * nct + g) & 1; ct < nct; ct += 2, ++use) {
+        float* hx = T->hx[g][use & 1];
+        if (et == 0) ECB_STAMP(2 + g, 4 * use);
         {
           const int j = ct * BN + et;
-          T->hx[as][et] = (j < N) ? -0.5f * xx[cloud_row0 + j] : -CUDART_INF_F;
+          hx[et] = (j < N) ? -0.5f * xx[cloud_row0 + j] : -CUDART_INF_F;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI) : "memory");  // epilogue warps only
-        mbar_wait(&T->t_full[as], (tile >> 1) & 1);
+        if (g == 0) asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI) : "memory");
+        else        asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI) : "memory");
+        if (et == 0) ECB_STAMP(2 + g, 4 * use + 1);
+        mbar_wait(&T->t_full[g], use & 1);
         tc_fence_after();
+        if (et == 0) ECB_STAMP(2 + g, 4 * use + 2);
+#pragma unroll 1
+        for (int c2 = 0; c2 < BN / 64; ++c2) {
 #pragma unroll
-        for (int c4 = 0; c4 < BN / 32; ++c4) {
-          float v[32];
-          __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned)
-          tmem_ld_32x32(lane_base + (uint32_t)(as * BN + c4 * 32), v);
-          const float4* hx4 = reinterpret_cast<const float4*>(&T->hx[as][c4 * 32]);
+          for (int hf = 0; hf < 2; ++hf) {
+            const int c4 = c2 * 2 + hf;
+            float v[32];
+            __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned)
+            tmem_ld_32x32(lane_base + (uint32_t)(c4 * 32), v);
+            const float4* hx4 = reinterpret_cast<const float4*>(hx + c4 * 32);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 h4 = hx4[g];
-            v[4 * g + 0] += h4.x; v[4 * g + 1] += h4.y; v[4 * g + 2] += h4.z; v[4 * g + 3] += h4.w;
-          }
-          if (DEBUG) {
-            if (valid) {
+            for (int e = 0; e < 8; ++e) {
+              const float4 h4 = hx4[e];
+              v[4 * e + 0] += h4.x; v[4 * e + 1] += h4.y; v[4 * e + 2] += h4.z; v[4 * e + 3] += h4.w;
+            }
+            if (DEBUG) {
+              if (valid) {
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                  const int j = ct * BN + c4 * 32 + u;
+                  if (j < N) dbg[((size_t)(cloud_row0 + row)) * N + j] = v[u];
+                }
+              }
+            } else if (pass == 0) {
 #pragma unroll
               for (int u = 0; u < 32; ++u) {
-                const int j = ct * BN + c4 * 32 + u;
-                if (j < N) dbg[((size_t)(cloud_row0 + row)) * N + j] = v[u];
+                const int bi = (NBINS == 64 ? hf * 32 : 0) + u;
+                bin[bi] = fmaxf(bin[bi], v[u]);
               }
-            }
-          } else if (pass == 0) {
-            constexpr int HALVES = NBINS / 32;
+            } else if (valid) {
+              // 16 candidates at a time: all scores go to the thread's column of a small
+              // shared-memory stage and a 16-bit pass mask is built -- independent, branch-
+              // free work; only rows that actually have a survivor (a few %) then walk
+              // their mask and append keys to the row's list in the L2-resident workspace.
 #pragma unroll
-            for (int u = 0; u < 32; ++u) {
-              const int bi = (c4 % HALVES) * 32 + u;
-              bin[bi] = fmaxf(bin[bi], v[u]);
-            }
-          } else if (valid) {
+              for (int h16 = 0; h16 < 2; ++h16) {
+                uint32_t mask = 0;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (cnt > cap - 8) {  // slow path: keep the row's own best k, raise the bar
-                while (cnt > k) {
-                  int arg = 0;
-                  uint64_t mn = mybuf[0];
-                  for (int e = 1; e < cnt; ++e) {
-                    const uint64_t w = mybuf[e];
-                    if (w < mn) { mn = w; arg = e; }
-                  }
-                  --cnt;
-                  mybuf[arg] = mybuf[cnt];
+                for (int u = 0; u < 16; ++u) {
+                  const float sc = v[h16 * 16 + u];
+                  stage_s[u * (2 * NUM_EPI)] = sc;
+                  mask |= (sc >= thr ? 1u : 0u) << u;
                 }
-                uint64_t mn = mybuf[0];
-                for (int e = 1; e < cnt; ++e) mn = min(mn, mybuf[e]);
-                thr = fmaxf(thr, nextafterf(key_score(mn), CUDART_INF_F));
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const float s = v[g * 8 + u];
-                if (s >= thr) {
-                  mybuf[cnt] = make_key(s, ct * BN + c4 * 32 + g * 8 + u);
-                  ++cnt;
+                if (mask) {
+                  if (cnt + 16 > cap) {  // slow path: keep this thread's own best k, raise the bar
+                    while (cnt > k) {
+                      int arg = 0;
+                      uint64_t mn = mybuf[0];
+                      for (int e = 1; e < cnt; ++e) {
+                        const uint64_t w = mybuf[e * LS];
+                        if (w < mn) { mn = w; arg = e; }
+                      }
+                      --cnt;
+                      mybuf[arg * LS] = mybuf[cnt * LS];
+                    }
+                    uint64_t mn = mybuf[0];
+                    for (int e = 1; e < cnt; ++e) mn = min(mn, mybuf[e * LS]);
+                    thr = fmaxf(thr, nextafterf(key_score(mn), CUDART_INF_F));
+                  }
+                  const int jb = ct * BN + c4 * 32 + h16 * 16;
+                  while (mask) {
+                    const int u = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float sc = stage_s[u * (2 * NUM_EPI)];
+                    if (sc >= thr) mybuf[(cnt++) * LS] = make_key(sc, jb + u);  // thr may just have risen
+                  }
                 }
               }
             }
           }
         }
         tc_fence_before();
-        mbar_arrive(&T->t_empty[as]);
+        mbar_arrive(&T->t_empty[g]);
+        if (et == 0) ECB_STAMP(2 + g, 4 * use + 3);
       }
+      if (et == 0) ECB_STAMP(4, 8 * g + pass);
     }
-    if (!DEBUG && valid) {
-      // exact top-k of the survivors: rank = number of strictly better keys = output slot
-      int32_t* out = idx + (size_t)(cloud_row0 + row) * k;
-      for (int p = cnt; p < k; ++p) out[p] = N - 1;  // only with NaN input
-      for (int e = 0; e < cnt; ++e) {
-        const uint64_t key = mybuf[e];
-        int rank = 0;
-        for (int f = 0; f < cnt; ++f) rank += (mybuf[f] > key);
-        if (rank < k) out[rank] = (int32_t)min(key_index(key), (uint32_t)(N - 1));
+    if (!DEBUG) {
+      // Exact top-k of the row's survivors (both groups): rank = number of strictly better
+      // keys = output slot.  Once both groups have passed their last t_full wait every MMA
+      // has completed and the operand tiles are dead, so the survivor lists move from the
+      // L2-resident workspace into conflict-free columns of that shared memory.
+      asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
+      if (et == 0) ECB_STAMP(4, 8 * g + 2);
+      const int me = g * NUM_EPI + et, other = (g ^ 1) * NUM_EPI + et;
+      uint64_t* cols = reinterpret_cast<uint64_t*>(base);  // [cap][2*NUM_EPI] keys
+      if (!valid) cnt = 0;
+      for (int e0 = 0; e0 < cnt; e0 += 8) {  // loads first, then stores: one L2 round trip per 8
+        uint64_t tmp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) tmp[u] = e0 + u < cnt ? __ldcg(mybuf + (e0 + u) * LS) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (e0 + u < cnt) cols[(e0 + u) * (2 * NUM_EPI) + me] = tmp[u];
       }
+      T->cnt_x[g][et] = cnt;
+      asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
+      if (et == 0) ECB_STAMP(4, 8 * g + 3);
+      if (valid) {
+        const int ocnt = T->cnt_x[g ^ 1][et];
+        int32_t* out = idx + (size_t)(cloud_row0 + row) * k;
+        if (g == 0)
+          for (int p = cnt + ocnt; p < k; ++p) out[p] = N - 1;  // only with NaN input
+        for (int e0 = 0; e0 < cnt; e0 += 8) {  // 8 own keys in registers per sweep of the union
+          uint64_t own[8];
+          int rank[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            own[u] = e0 + u < cnt ? cols[(e0 + u) * (2 * NUM_EPI) + me] : ~0ull;
+            rank[u] = 0;
+          }
+          for (int f = 0; f < cnt; ++f) {
+            const uint64_t kf = cols[f * (2 * NUM_EPI) + me];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) rank[u] += (kf > own[u]);
+          }
+          for (int f = 0; f < ocnt; ++f) {
+            const uint64_t kf = cols[f * (2 * NUM_EPI) + other];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) rank[u] += (kf > own[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (e0 + u < cnt && rank[u] < k)
+              out[rank[u]] = (int32_t)min(key_index(own[u]), (uint32_t)(N - 1));
+        }
+      }
+      if (et == 0) ECB_STAMP(4, 8 * g + 4);
     }
   }
 
@@ -347,7 +454,7 @@ int make_point_map(CUtensorMap* m, const float* p, long long rows, int C) {
 
 template <int NBINS, bool DEBUG>
 int launch_tc(const float* hi, const float* lo, const float* xx, int B, int C, int N, int k,
-              uint64_t* ws, int cap, int32_t* idx, float* dbg, cudaStream_t st) {
+              uint64_t* ws, int cap, int32_t* idx, float* dbg, cudaStream_t st, long long* tl = nullptr) {
   const int nkb = C / KB;
   CUtensorMap mh, ml;
   int rc = make_point_map(&mh, hi, (long long)B * N, C);
@@ -360,7 +467,10 @@ int launch_tc(const float* hi, const float* lo, const float* xx, int B, int C, i
     ECB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_bytes(MAX_KB)));
   dim3 grid(ecb200::ceil_div(N, BM), B);
-  kern<<<grid, NT, smem_bytes(nkb), st>>>(mh, ml, xx, N, nkb, k, ws, cap, idx, dbg);
+  // workspace = survivor keys [tiles][cap][2][128] followed by the bin exchange [tiles][KMAX][2][128]
+  const size_t tiles = (size_t)B * ecb200::ceil_div(N, BM);
+  float* exch = ws ? reinterpret_cast<float*>(ws + tiles * (size_t)cap * 2 * NUM_EPI) : nullptr;
+  kern<<<grid, NT, smem_bytes(nkb), st>>>(mh, ml, xx, N, nkb, k, ws, exch, cap, idx, dbg, tl);
   ECB_LAUNCH_CHECK("knn_tc_kernel");
   return ECB200_OK;
 }
@@ -377,12 +487,15 @@ extern "C" int ecb200_split_tf32(const float* x, int B, int C, int N, float* hi,
   return ECB200_OK;
 }
 
-// survivor slots per row in the workspace (expected use: ~31 at k = 20 with 32 bins, ~63 at
-// k = 40 with 64 bins; overflow falls back to an exact in-place shrink)
-static int survivor_cap(int k) { return k <= 20 ? 96 : 160; }
+// survivor slots per (row, epilogue group) in the workspace (2 x 32 pooled bins per row:
+// expected use ~12 per thread at k = 20, ~32 at k = 40; overflow falls back to an exact
+// in-place shrink, so cap >= k + 16).  cap * 256 threads * 8 bytes must fit the >= 160 KB of operand tiles that the
+// final ranking reuses.
+static int survivor_cap(int k) { return k <= 20 ? 48 : 80; }
 
 extern "C" size_t ecb200_knn_tc_workspace_bytes(int B, int N, int k) {
-  return (size_t)B * N * (size_t)survivor_cap(k) * sizeof(uint64_t);
+  const size_t tiles = (size_t)B * ecb200::ceil_div(N, BM);
+  return tiles * 2 * NUM_EPI * ((size_t)survivor_cap(k) * sizeof(uint64_t) + KMAX * sizeof(float));
 }
 
 extern "C" int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, int B, int C, int N,
@@ -394,15 +507,22 @@ extern "C" int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, 
   ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB,
               "ecb200_knn_tc: C=%d must be a multiple of 32 in [32, 128]", C);
   ECB_REQUIRE(k >= 1 && k <= N, "ecb200_knn_tc: k=%d out of range for N=%d (selected index k out of range)", k, N);
-  ECB_REQUIRE(k <= 40, "ecb200_knn_tc: k=%d exceeds 40 (use ecb200_knn)", k);
+  ECB_REQUIRE(k <= KMAX, "ecb200_knn_tc: k=%d exceeds %d (use ecb200_knn)", k, KMAX);
   ECB_REQUIRE(workspace_bytes >= ecb200_knn_tc_workspace_bytes(B, N, k),
               "ecb200_knn_tc: workspace too small (%zu < %zu bytes)", workspace_bytes,
               ecb200_knn_tc_workspace_bytes(B, N, k));
   const int cap = survivor_cap(k);
   cudaStream_t st = (cudaStream_t)stream;
-  if (k <= 20)
-    return launch_tc<32, false>(hi, lo, xx, B, C, N, k, (uint64_t*)workspace, cap, idx, nullptr, st);
-  return launch_tc<64, false>(hi, lo, xx, B, C, N, k, (uint64_t*)workspace, cap, idx, nullptr, st);
+  return launch_tc<32, false>(hi, lo, xx, B, C, N, k, (uint64_t*)workspace, cap, idx, nullptr, st);
+}
+
+extern "C" int ecb200_debug_tc_timeline(const float* hi, const float* lo, const float* xx, int B, int C,
+                                        int N, int k, int32_t* idx, void* workspace,
+                                        long long* timeline, void* stream) {
+  ECB_REQUIRE(hi && lo && xx && idx && workspace && timeline, "ecb200_debug_tc_timeline: null pointer");
+  ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB && k <= 40 && k <= N, "bad shape");
+  return launch_tc<32, false>(hi, lo, xx, B, C, N, k, (uint64_t*)workspace, survivor_cap(k), idx, nullptr,
+                              (cudaStream_t)stream, timeline);
 }
 
 extern "C" int ecb200_debug_tc_scores(const float* hi, const float* lo, const float* xx, int B, int C,

@@ -94,6 +94,9 @@ int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, int B, int 
                   void* stream);
 int ecb200_debug_tc_scores(const float* hi, const float* lo, const float* xx, int B, int C, int N,
                            float* scores, void* stream);
+/* diagnostic: ecb200_knn_tc with CTA (0,0) stamping clock64() into timeline[6*256] (int64) */
+int ecb200_debug_tc_timeline(const float* hi, const float* lo, const float* xx, int B, int C, int N,
+                             int k, int32_t* idx, void* workspace, long long* timeline, void* stream);
 
 /* ---- materialised graph feature: replaces get_graph_feature(), dgcnn.py:15-44 ------ */
 int ecb200_graph_feature(const float* x, const int32_t* idx, int B, int C, int N, int k,

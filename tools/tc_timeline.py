@@ -1,0 +1,37 @@
+"""Per-role clock64() timeline of CTA (0,0) of the tensor-core kNN kernel."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+from ctypes import c_void_p
+import torch
+import dgcnn_pytorch_b200 as ec
+import edgeconv_oracle as orc
+L = ec._lib
+B, C, N, k = (int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "32,64,1024,20".split(",")))
+dev = torch.device("cuda:0")
+x = orc.synthetic_features(B, C, N, seed=1).to(dev)
+hi = torch.empty(B * N, C, device=dev); lo = torch.empty_like(hi); xx = torch.empty(B * N, device=dev)
+idx = torch.empty(B, N, k, device=dev, dtype=torch.int32)
+nb = L.load().ecb200_knn_tc_workspace_bytes(B, N, k)
+ws = torch.empty(nb, device=dev, dtype=torch.uint8)
+tl = torch.zeros(6 * 256, device=dev, dtype=torch.int64)
+P = lambda t: c_void_p(t.data_ptr())
+st = c_void_p(torch.cuda.current_stream().cuda_stream)
+L.call("ecb200_split_tf32", P(x), B, C, N, P(hi), P(lo), P(xx), st)
+for _ in range(3):
+    L.call("ecb200_debug_tc_timeline", P(hi), P(lo), P(xx), B, C, N, k, P(idx), P(ws), P(tl), st)
+torch.cuda.synchronize()
+t = tl.cpu().view(6, 256)
+t0 = int(t[5, 0])
+nct = (N + 127) // 128; nkb = C // 32
+rel = lambda v: (int(v) - t0) if int(v) else None
+print("producer stage-acquire times (first 20, last 4):", [rel(v) for v in t[0, :20]], [rel(v) for v in t[0, 2 * nct * nkb - 4:2 * nct * nkb]])
+print("mma per tile (start, commit):")
+for i in range(2 * nct):
+    print("   tile", i, rel(t[1, 2 * i]), rel(t[1, 2 * i + 1]))
+for g in (0, 1):
+    print(f"epilogue group {g}: per use (begin, hx-barrier done, t_full acquired, done)")
+    for u in range(nct):
+        print("   use", u, [rel(v) for v in t[2 + g, 4 * u:4 * u + 4]])
+    print("   pass ends / pre-copy / post-copy / ranked:", [rel(v) for v in t[4, 8 * g:8 * g + 5]])
+    print("   tau stage: start / sorted / done:", [rel(v) for v in t[4, 8 * g + 5:8 * g + 8]])
