@@ -8,5 +8,6 @@ from . import _lib, ops
 from .dgcnn import DGCNN, edgeconv_block, get_graph_feature, knn
 from .model import ClsHead, DGCNN_cls, cal_loss
 from .ops import edgeconv
+from .runtime import GraphedTrainStep
 
-__all__ = ["DGCNN", "DGCNN_cls", "ClsHead", "cal_loss", "edgeconv", "edgeconv_block", "get_graph_feature", "knn", "ops", "_lib"]
+__all__ = ["DGCNN", "GraphedTrainStep", "DGCNN_cls", "ClsHead", "cal_loss", "edgeconv", "edgeconv_block", "get_graph_feature", "knn", "ops", "_lib"]
