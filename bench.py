@@ -206,6 +206,12 @@ class EntryTimer:
         return out
 
 
+def note(msg):
+    """progress notes on stderr (BENCH_DEBUG=1)"""
+    if os.environ.get("BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def edge_layer_shapes(a):
     """(C, Co) of the four EdgeConv layers (models/dgcnn.py:54-73)."""
     return [(3, 64), (64, 64), (64, 128), (128, 256)]
@@ -230,12 +236,19 @@ def run_b200(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything libraries print there (e.g. the NCCL
+    # version banner) is routed to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); "
                            "use --impl reference for the CPU reference arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # collectives get graph-captured
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     B = a.batch if a.scaling == "weak" else max(1, a.batch // world)
     N, k = a.points, a.k
@@ -243,9 +256,15 @@ def run_b200(a):
     torch.manual_seed(1)
     args = SimpleNamespace(emb_dim=a.emb, k=k, dropout=0.5)
     model = ec.DGCNN_cls(args).to(dev).train()
+    sync = None
     if world > 1:
+        # SyncBatchNorm semantics for every BN (the EdgeConv ones exchange their statistics
+        # inside the fused op); gradients averaged by one flat all-reduce per step
+        from dgcnn_pytorch_b200.dist import FlatGradSync
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+        for p in model.parameters():          # identical replicas
+            dist.broadcast(p.data, 0)
+        sync = FlatGradSync(model.parameters())
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
 
     import edgeconv_oracle as orc   # only for the synthetic-input generator and the cpu_baseline leg
@@ -258,9 +277,14 @@ def run_b200(a):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step(x, y):
-        opt.zero_grad(set_to_none=True)
+        if sync is not None:
+            sync.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
         loss = ec.cal_loss(model(x), y)
         loss.backward()
+        if sync is not None:
+            sync.average()
         opt.step()
         return loss
 
@@ -280,9 +304,11 @@ def run_b200(a):
     ec._lib.set_event_hook(timer)
 
     # ---- warm-up (also sizes the allocator pools and opts kernels into big smem)
+    note("warm-up")
     for i in range(max(3, a.warmup)):
         step(dev_x[i % npool], dev_y[i % npool])
     barrier()
+    note("warm-up done")
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -312,13 +338,15 @@ def run_b200(a):
     timer.enabled = False
     eager_ms = reduce_max(eager_ms)
     entries = timer.summary()
+    note(f"eager timed: {eager_ms:.3f} ms/step")
 
     # ---- timed region B: the same step captured once into a CUDA graph and replayed
     #      (dgcnn_pytorch_b200.GraphedTrainStep, the package's public way to run a step)
     graph_ms, graph_err, gstep = None, None, None
     if not a.no_graph:
         try:
-            gstep = ec.GraphedTrainStep(model, opt, ec.cal_loss, dev_x[0], dev_y[0])
+            gstep = ec.GraphedTrainStep(model, opt, ec.cal_loss, dev_x[0], dev_y[0], grad_sync=sync)
+            note("graph captured")
             for i in range(3):
                 gstep(dev_x[i % npool], dev_y[i % npool])
             graph_ms = reduce_max(timed(lambda i: gstep(dev_x[i % npool], dev_y[i % npool]), a.steps))
@@ -326,6 +354,7 @@ def run_b200(a):
             graph_err = f"{type(exc).__name__}: {exc}"[:200]
             gstep = None
             torch.cuda.synchronize()
+    note(f"graph timed: {graph_ms} ms/step, error {graph_err}")
     use_graph = graph_ms is not None and graph_ms < eager_ms
     best_ms = graph_ms if use_graph else eager_ms
 
@@ -336,20 +365,23 @@ def run_b200(a):
         if use_graph:
             return gstep(hx, hy).item()
         return step(hx.to(dev, non_blocking=True), hy.to(dev, non_blocking=True)).item()
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(a.steps):
-        e2e_step(i)
-    barrier()
-    e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3 / a.steps)
+    e2e_ms, e2e_err = float("nan"), None
+    try:
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(a.steps):
+            e2e_step(i)
+        barrier()
+        e2e_ms = reduce_max((time.perf_counter() - t0) * 1e3 / a.steps)
+    except Exception as exc:  # noqa: BLE001 - reported in the JSON line
+        e2e_err = f"{type(exc).__name__}: {exc}"[:200]
     t_clock1 = time.perf_counter()
     clocks = sampler.stop(t_clock0, t_clock1) if rank == 0 else None
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
 
     pk = peaks()
@@ -388,19 +420,33 @@ def run_b200(a):
                    "l2": "256 MiB buffer rewritten between timed steps (L2 flush)",
                    "cuda_graph": use_graph,
                    "eager_ms_per_step": eager_ms, "graph_ms_per_step": graph_ms,
-                   "graph_error": graph_err, "conv5_and_head": "torch (cuDNN/cuBLAS, library defaults)"},
+                   "graph_error": graph_err, "conv5_and_head": "torch (cuDNN/cuBLAS, library defaults)",
+                   "grad_sync": "one flat NCCL all-reduce per step" if world > 1 else None},
         "clocks": clocks,
         "e2e": {"value": clouds / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "error": e2e_err},
         "gpu_launches": int(round(launches_per_step * a.steps)),
         "gpu_launches_per_step": launches_per_step,
         "roofline": roof,
         "kernel_ms_per_step": breakdown,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
+    finish(world)
+
+
+def finish(world):
+    """Leave without tearing NCCL down: communicators referenced by captured CUDA graphs can
+    make destroy_process_group() wait forever, so multi-rank runs exit hard once every rank
+    has finished (the JSON line is already flushed)."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -54,3 +54,35 @@ def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     return stats
+
+
+class FlatGradSync:
+    """Data-parallel gradient averaging as ONE all-reduce of a flat fp32 buffer.
+
+    Every parameter's ``.grad`` is a view into ``self.flat``; autograd accumulates into the
+    views in place, so after ``backward()`` a single NCCL all-reduce (over NVLink / NVSwitch,
+    NVLS when available) on the compute stream averages all gradients -- no bucketing
+    threads, no hooks, and the call is capturable in a CUDA graph together with the step.
+    DGCNN-cls has 1.8 M parameters (7 MB): latency, not bandwidth, is what matters here.
+    Usage per step:  sync.zero() ; loss.backward() ; sync.average() ; optimizer.step()
+    """
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        o = 0
+        for p in self.params:
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def average(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / self.world)

@@ -18,10 +18,14 @@ import torch
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer,
                  loss_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
-                 example_x: torch.Tensor, example_y: torch.Tensor, warmup: int = 3):
+                 example_x: torch.Tensor, example_y: torch.Tensor, warmup: int = 3,
+                 grad_sync=None):
+        """``grad_sync``: optional dist.FlatGradSync for data-parallel runs (its all-reduce is
+        captured with the step)."""
         if not example_x.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA example tensors (no CPU fallback)")
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
+        self.grad_sync = grad_sync
         self.x = example_x.clone()
         self.y = example_y.clone()
         # warm-up on a side stream: sizes allocator pools, opts kernels into large shared memory
@@ -33,15 +37,22 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
+        if grad_sync is None:
+            self.optimizer.zero_grad(set_to_none=True)
+        # thread_local: NCCL's watchdog thread may query events while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = self._eager()
         torch.cuda.synchronize()
 
     def _eager(self) -> torch.Tensor:
-        self.optimizer.zero_grad(set_to_none=True)
+        if self.grad_sync is not None:
+            self.grad_sync.zero()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
         loss = self.loss_fn(self.model(self.x), self.y)
         loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync.average()
         self.optimizer.step()
         return loss.detach()
 
