@@ -396,8 +396,13 @@ def run_b200(a):
         by = sum(gather_bytes(M, k, co) for _, co in edge_layer_shapes(a))
         t_ms = gather["total_ms"] / a.steps
         ach = by / (t_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_gather_traffic.json")
+        if (a.batch, a.points, a.k) == (32, 1024, 20) and os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)["dram_bytes_per_step"]     # ncu --set full capture, per step
         roof = {"bound": "hbm", "kernel": "edge_gather_kernel", "achieved": ach, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic,
                 "peak_source": pk["source"], "launches_per_step": per_step_calls,
                 "algorithmic_bytes_per_step": by, "ms_per_step": t_ms}
     breakdown = {n: round(v["total_ms"] / a.steps, 4) for n, v in
