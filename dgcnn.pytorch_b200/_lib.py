@@ -8,12 +8,12 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_double, c_float, c_int, c_size_t, c_void_p
+from ctypes import c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libedgeconv_b200.so")
 
-P, I, F, D, Z = c_void_p, c_int, c_float, c_double, c_size_t
+P, I, F, D, Z, LL = c_void_p, c_int, c_float, c_double, c_size_t, c_longlong
 
 # name -> argument types, in the order of include/edgeconv_b200.h (all return int)
 SIGNATURES = {
@@ -23,6 +23,8 @@ SIGNATURES = {
     "ecb200_knn_tc": (P, P, P, I, I, I, I, I, P, P, Z, P),
     "ecb200_debug_tc_scores": (P, P, P, I, I, I, P, P),
     "ecb200_debug_tc_timeline": (P, P, P, I, I, I, I, P, P, P, P),
+    "ecb200_split_rows_tf32": (P, LL, P, P, P),
+    "ecb200_point_gemm_tc": (P, P, P, P, LL, I, I, P, P),
     "ecb200_graph_feature": (P, P, I, I, I, I, I, P, P),
     "ecb200_graph_feature_bwd": (P, P, I, I, I, I, I, P, P),
     "ecb200_pack_weight": (P, I, I, I, P, P),

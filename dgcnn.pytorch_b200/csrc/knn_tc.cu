@@ -81,9 +81,13 @@ __device__ __forceinline__ void sort_bins_desc(float (&v)[NBINS]) {
 template <int NBINS, bool DEBUG>
 __global__ void __launch_bounds__(NT, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-              const float* __restrict__ xx, int N, int nkb, int k, uint64_t* __restrict__ surv_ws,
-              float* __restrict__ exch, int cap, int32_t* __restrict__ idx, float* __restrict__ dbg,
-              long long* tl) {
+              const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+              const float* __restrict__ xx, int Na, int N, int nkb, int k,
+              uint64_t* __restrict__ surv_ws, float* __restrict__ exch, int cap,
+              int32_t* __restrict__ idx, float* __restrict__ dbg, long long* tl) {
+  // A operand: rows [b*Na + rt*128, +128) of map_hi/lo (the queries; for the GEMM use the points).
+  // B operand: rows [b*N + ct*128, +128) of map_bhi/blo (the candidates; for the GEMM the rows of
+  // Wcat).  kNN passes the same maps twice and Na == N.
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round-trip
   // would turn every later access into a generic-address load/store)
@@ -98,11 +102,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const int b = blockIdx.y, rt = blockIdx.x;
   const int nct = (N + BN - 1) / BN;
   const int npass = DEBUG ? 1 : 2;
-  const int cloud_row0 = b * N;  // first global row of this cloud in the [M, C] arrays
+  const int cloud_row0 = b * N;   // first global B row of this cloud
+  const int a_row0 = b * Na;      // first global A row of this cloud
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_hi);
     prefetch_tensormap(&map_lo);
+    prefetch_tensormap(&map_bhi);
+    prefetch_tensormap(&map_blo);
     mbar_init(&T->a_full, 1);
     for (int s = 0; s < S; ++s) { mbar_init(&T->b_full[s], 1); mbar_init(&T->b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&T->t_full[s], 1); mbar_init(&T->t_empty[s], NUM_EPI); }
@@ -120,8 +127,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     if (lane == 0) {
       mbar_expect_tx(&T->a_full, (uint32_t)(2 * nkb * TILE_BYTES));
       for (int kb = 0; kb < nkb; ++kb) {
-        tma_load_2d(a_hi + (size_t)kb * TILE_BYTES, &map_hi, &T->a_full, kb * KB, cloud_row0 + rt * BM);
-        tma_load_2d(a_lo + (size_t)kb * TILE_BYTES, &map_lo, &T->a_full, kb * KB, cloud_row0 + rt * BM);
+        tma_load_2d(a_hi + (size_t)kb * TILE_BYTES, &map_hi, &T->a_full, kb * KB, a_row0 + rt * BM);
+        tma_load_2d(a_lo + (size_t)kb * TILE_BYTES, &map_lo, &T->a_full, kb * KB, a_row0 + rt * BM);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -132,8 +139,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             ECB_STAMP(0, (pass * nct + ct) * nkb + kb);
             unsigned char* dst = b_st + (size_t)stage * 2 * TILE_BYTES;
             mbar_expect_tx(&T->b_full[stage], 2 * TILE_BYTES);
-            tma_load_2d(dst, &map_hi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
-            tma_load_2d(dst + TILE_BYTES, &map_lo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+            tma_load_2d(dst, &map_bhi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+            tma_load_2d(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
     }
@@ -185,7 +192,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int et = (threadIdx.x - 64) & (NUM_EPI - 1);
     const int row = rt * BM + q * 32 + lane;
-    const bool valid = row < N;
+    const bool valid = row < Na;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN);
     float bin[NBINS];
 #pragma unroll
@@ -233,7 +240,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         if (et == 0) ECB_STAMP(2 + g, 4 * use);
         {
           const int j = ct * BN + et;
-          hx[et] = (j < N) ? -0.5f * xx[cloud_row0 + j] : -CUDART_INF_F;
+          hx[et] = xx ? ((j < N) ? -0.5f * xx[cloud_row0 + j] : -CUDART_INF_F) : 0.f;
         }
         if (g == 0) asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI) : "memory");
         else        asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI) : "memory");
@@ -255,12 +262,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
               const float4 h4 = hx4[e];
               v[4 * e + 0] += h4.x; v[4 * e + 1] += h4.y; v[4 * e + 2] += h4.z; v[4 * e + 3] += h4.w;
             }
-            if (DEBUG) {
+            if (DEBUG) {  // dense store of the tile: raw scores, or the GEMM result Y = A.B^T
               if (valid) {
+                float* orow = dbg + ((size_t)(a_row0 + row)) * N + ct * BN + c4 * 32;
+                if ((N & 3) == 0) {
 #pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                  const int j = ct * BN + c4 * 32 + u;
-                  if (j < N) dbg[((size_t)(cloud_row0 + row)) * N + j] = v[u];
+                  for (int e = 0; e < 8; ++e)
+                    if (ct * BN + c4 * 32 + 4 * e < N)
+                      *reinterpret_cast<float4*>(orow + 4 * e) =
+                          make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                } else {
+#pragma unroll
+                  for (int u = 0; u < 32; ++u)
+                    if (ct * BN + c4 * 32 + u < N) orow[u] = v[u];
                 }
               }
             } else if (pass == 0) {
@@ -452,27 +466,45 @@ int make_point_map(CUtensorMap* m, const float* p, long long rows, int C) {
   return ECB200_OK;
 }
 
+// [rows, C] fp32 row-major operand pair (hi, lo) as TMA maps
+struct OperandMaps {
+  CUtensorMap hi, lo;
+};
+int make_operand(OperandMaps* m, const float* hi, const float* lo, long long rows, int C) {
+  int rc = make_point_map(&m->hi, hi, rows, C);
+  if (rc) return rc;
+  return make_point_map(&m->lo, lo, rows, C);
+}
+
+// clouds = grid.y; per cloud Na rows of A (queries / points) and Nb rows of B (candidates / Wcat rows)
 template <int NBINS, bool DEBUG>
-int launch_tc(const float* hi, const float* lo, const float* xx, int B, int C, int N, int k,
-              uint64_t* ws, int cap, int32_t* idx, float* dbg, cudaStream_t st, long long* tl = nullptr) {
+int launch_tc(const OperandMaps& A, const OperandMaps& Bm, const float* xx, int clouds, int C, int Na,
+              int Nb, int k, uint64_t* ws, int cap, int32_t* idx, float* dbg, cudaStream_t st,
+              long long* tl = nullptr) {
   const int nkb = C / KB;
-  CUtensorMap mh, ml;
-  int rc = make_point_map(&mh, hi, (long long)B * N, C);
-  if (rc) return rc;
-  rc = make_point_map(&ml, lo, (long long)B * N, C);
-  if (rc) return rc;
   auto kern = knn_tc_kernel<NBINS, DEBUG>;
   static thread_local bool seen[ecb200::kMaxDevices] = {};
   if (ecb200::first_use_on_device(seen))
     ECB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_bytes(MAX_KB)));
-  dim3 grid(ecb200::ceil_div(N, BM), B);
+  dim3 grid(ecb200::ceil_div(Na, BM), clouds);
   // workspace = survivor keys [tiles][cap][2][128] followed by the bin exchange [tiles][KMAX][2][128]
-  const size_t tiles = (size_t)B * ecb200::ceil_div(N, BM);
+  const size_t tiles = (size_t)clouds * ecb200::ceil_div(Na, BM);
   float* exch = ws ? reinterpret_cast<float*>(ws + tiles * (size_t)cap * 2 * NUM_EPI) : nullptr;
-  kern<<<grid, NT, smem_bytes(nkb), st>>>(mh, ml, xx, N, nkb, k, ws, exch, cap, idx, dbg, tl);
+  kern<<<grid, NT, smem_bytes(nkb), st>>>(A.hi, A.lo, Bm.hi, Bm.lo, xx, Na, Nb, nkb, k, ws, exch, cap, idx,
+                                          dbg, tl);
   ECB_LAUNCH_CHECK("knn_tc_kernel");
   return ECB200_OK;
+}
+
+__global__ void split_rows_tf32_kernel(const float* __restrict__ src, long long n, float* __restrict__ hi,
+                                       float* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = src[i];
+  const float h = to_tf32(v);
+  hi[i] = h;
+  lo[i] = to_tf32(v - h);
 }
 
 }  // namespace
@@ -511,17 +543,22 @@ extern "C" int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, 
   ECB_REQUIRE(workspace_bytes >= ecb200_knn_tc_workspace_bytes(B, N, k),
               "ecb200_knn_tc: workspace too small (%zu < %zu bytes)", workspace_bytes,
               ecb200_knn_tc_workspace_bytes(B, N, k));
-  const int cap = survivor_cap(k);
-  cudaStream_t st = (cudaStream_t)stream;
-  return launch_tc<32, false>(hi, lo, xx, B, C, N, k, (uint64_t*)workspace, cap, idx, nullptr, st);
+  OperandMaps X;
+  int rc = make_operand(&X, hi, lo, (long long)B * N, C);
+  if (rc) return rc;
+  return launch_tc<32, false>(X, X, xx, B, C, N, N, k, (uint64_t*)workspace, survivor_cap(k), idx, nullptr,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int ecb200_debug_tc_timeline(const float* hi, const float* lo, const float* xx, int B, int C,
                                         int N, int k, int32_t* idx, void* workspace,
                                         long long* timeline, void* stream) {
   ECB_REQUIRE(hi && lo && xx && idx && workspace && timeline, "ecb200_debug_tc_timeline: null pointer");
-  ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB && k <= 40 && k <= N, "bad shape");
-  return launch_tc<32, false>(hi, lo, xx, B, C, N, k, (uint64_t*)workspace, survivor_cap(k), idx, nullptr,
+  ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB && k <= KMAX && k <= N, "bad shape");
+  OperandMaps X;
+  int rc = make_operand(&X, hi, lo, (long long)B * N, C);
+  if (rc) return rc;
+  return launch_tc<32, false>(X, X, xx, B, C, N, N, k, (uint64_t*)workspace, survivor_cap(k), idx, nullptr,
                               (cudaStream_t)stream, timeline);
 }
 
@@ -531,5 +568,30 @@ extern "C" int ecb200_debug_tc_scores(const float* hi, const float* lo, const fl
   ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1, "ecb200_debug_tc_scores: bad shape");
   ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB,
               "ecb200_debug_tc_scores: C=%d must be a multiple of 32 in [32, 128]", C);
-  return launch_tc<32, true>(hi, lo, xx, B, C, N, 1, nullptr, 0, nullptr, scores, (cudaStream_t)stream);
+  OperandMaps X;
+  int rc = make_operand(&X, hi, lo, (long long)B * N, C);
+  if (rc) return rc;
+  return launch_tc<32, true>(X, X, xx, B, C, N, N, 1, nullptr, 0, nullptr, scores, (cudaStream_t)stream);
+}
+
+extern "C" int ecb200_split_rows_tf32(const float* src, long long n, float* hi, float* lo, void* stream) {
+  ECB_REQUIRE(src && hi && lo && n >= 1, "ecb200_split_rows_tf32: bad arguments");
+  split_rows_tf32_kernel<<<(unsigned)ecb200::ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(src, n, hi, lo);
+  ECB_LAUNCH_CHECK("split_rows_tf32_kernel");
+  return ECB200_OK;
+}
+
+extern "C" int ecb200_point_gemm_tc(const float* xhi, const float* xlo, const float* whi, const float* wlo,
+                                    long long M, int C, int Co2, float* Y, void* stream) {
+  ECB_REQUIRE(xhi && xlo && whi && wlo && Y, "ecb200_point_gemm_tc: null pointer");
+  ECB_REQUIRE(M >= 1 && M < (1LL << 31) && Co2 >= 1, "ecb200_point_gemm_tc: bad shape");
+  ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB,
+              "ecb200_point_gemm_tc: C=%d must be a multiple of 32 in [32, 128]", C);
+  OperandMaps X, W;
+  int rc = make_operand(&X, xhi, xlo, M, C);
+  if (rc) return rc;
+  rc = make_operand(&W, whi, wlo, Co2, C);
+  if (rc) return rc;
+  // one "cloud": A = all M points, B = the 2Co rows of Wcat, dense store of the tiles into Y[M, 2Co]
+  return launch_tc<32, true>(X, W, nullptr, 1, C, (int)M, Co2, 1, nullptr, 0, nullptr, Y, (cudaStream_t)stream);
 }

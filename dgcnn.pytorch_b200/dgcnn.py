@@ -78,6 +78,14 @@ def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
     if conv.bias is not None or tuple(conv.kernel_size) != (1, 1):
         raise RuntimeError("edgeconv_block expects a bias-free 1x1 Conv2d")
     x = _as_f32(x)
+    B, C, N = x.shape
+    xhi = xlo = None
+    if ops.knn_uses_tensor_cores(C, N, int(k)) or (idx is not None and ops.point_gemm_uses_tensor_cores(C)):
+        # feature-space layer: one split into tf32 hi/lo operands feeds both the tensor-core
+        # kNN and the tensor-core per-point GEMM
+        xhi, xlo, xx = ops.split_tf32_op(x.detach().contiguous())
+        if idx is None:
+            idx = ops.knn_tc_op(xhi, xlo, xx, B, N, int(k))
     if idx is None:
         idx = ops.knn_op(x.detach().contiguous(), int(k), False)   # order over k is irrelevant here
     group = 0
@@ -89,7 +97,7 @@ def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
     slope = float(getattr(act, "negative_slope", 0.0))
     out = ops.edgeconv(x, idx, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                        bn.num_batches_tracked, bn.training, bn.momentum, bn.eps, slope,
-                       subtract_center, group)
+                       subtract_center, group, xhi, xlo)
     return out, idx
 
 

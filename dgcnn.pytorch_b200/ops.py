@@ -80,18 +80,54 @@ def knn_op(x: Tensor, k: int, sorted: bool = True) -> Tensor:
         st = _stream(x)
         if knn_uses_tensor_cores(C, N, k):
             # feature-space layers: tcgen05 / TMA distance tiles (knn_tc.cu)
-            hi = torch.empty(B * N, C, device=x.device, dtype=torch.float32)
-            lo = torch.empty(B * N, C, device=x.device, dtype=torch.float32)
-            nbytes = _lib.load().ecb200_knn_tc_workspace_bytes(B, N, k)
-            ws = torch.empty(nbytes, device=x.device, dtype=torch.uint8)
-            _lib.call("ecb200_split_tf32", _ptr(x), B, C, N, _ptr(hi), _ptr(lo), _ptr(xx), st)
-            _lib.call("ecb200_knn_tc", _ptr(hi), _ptr(lo), _ptr(xx), B, C, N, k, int(sorted), _ptr(idx),
-                      _ptr(ws), nbytes, st)
+            hi, lo, xx = split_tf32_op(x)
+            return knn_tc_op(hi, lo, xx, B, N, k)
         else:
             # xyz layer (and any shape the tensor-core kernel does not take): FP32 FMA tiles
             _lib.call("ecb200_sqnorms", _ptr(x), B, C, N, _ptr(xx), st)
             _lib.call("ecb200_knn", _ptr(x), _ptr(xx), B, C, N, k, int(sorted), _ptr(idx), st)
     return idx
+
+
+@torch.library.custom_op("edgeconv_b200::split_tf32", mutates_args=(), device_types="cuda")
+def split_tf32_op(x: Tensor) -> List[Tensor]:
+    """x [B,C,N] -> [hi [B*N,C], lo [B*N,C], xx [B*N]]: the point-major tf32 operand pair shared
+    by the tensor-core kNN and the tensor-core point GEMM of a layer, and |x|^2."""
+    _check_cuda_f32("x", x, 3)
+    B, C, N = x.shape
+    x = x.contiguous()
+    with torch.cuda.device(x.device):
+        hi = torch.empty(B * N, C, device=x.device, dtype=torch.float32)
+        lo = torch.empty(B * N, C, device=x.device, dtype=torch.float32)
+        xx = torch.empty(B * N, device=x.device, dtype=torch.float32)
+        _lib.call("ecb200_split_tf32", _ptr(x), B, C, N, _ptr(hi), _ptr(lo), _ptr(xx), _stream(x))
+    return [hi, lo, xx]
+
+
+@split_tf32_op.register_fake
+def _(x):
+    B, C, N = x.shape
+    return [x.new_empty((B * N, C)), x.new_empty((B * N, C)), x.new_empty((B * N,))]
+
+
+@torch.library.custom_op("edgeconv_b200::knn_tc", mutates_args=(), device_types="cuda")
+def knn_tc_op(hi: Tensor, lo: Tensor, xx: Tensor, B: int, N: int, k: int) -> Tensor:
+    """kNN graph from the split operands: int32 [B,N,k], nearest first."""
+    C = hi.shape[1]
+    if k > N or k < 1:
+        raise RuntimeError(f"selected index k out of range (k={k}, N={N})")
+    with torch.cuda.device(hi.device):
+        idx = torch.empty(B, N, k, device=hi.device, dtype=torch.int32)
+        nbytes = _lib.load().ecb200_knn_tc_workspace_bytes(B, N, k)
+        ws = torch.empty(nbytes, device=hi.device, dtype=torch.uint8)
+        _lib.call("ecb200_knn_tc", _ptr(hi), _ptr(lo), _ptr(xx), B, C, N, k, 1, _ptr(idx), _ptr(ws), nbytes,
+                  _stream(hi))
+    return idx
+
+
+@knn_tc_op.register_fake
+def _(hi, lo, xx, B, N, k):
+    return hi.new_empty((B, N, k), dtype=torch.int32)
 
 
 def knn_uses_tensor_cores(C: int, N: int, k: int) -> bool:
@@ -193,7 +229,8 @@ graph_feature_op.register_autograd(_gf_backward, setup_context=_gf_setup)
 def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor,
                     running_mean: Optional[Tensor], running_var: Optional[Tensor],
                     use_batch_stats: bool, eps: float, slope: float, subtract_center: bool,
-                    group: int, save_for_bwd: bool) -> List[Tensor]:
+                    group: int, save_for_bwd: bool, xhi: Optional[Tensor],
+                    xlo: Optional[Tensor]) -> List[Tensor]:
     """Returns [out, sel, arg, esum, Y, Wcat, affine, stats]; ``affine`` is [4,Co] =
     (mean, invstd, a, b).  Everything after ``out`` exists for the backward pass."""
     _check_cuda_f32("x", x, 3)
@@ -223,7 +260,14 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
         mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * Co * r) for r in range(4))
         out = torch.empty(B, Co, N, **f32)
         _lib.call("ecb200_pack_weight", _ptr(w), Co, C, int(subtract_center), _ptr(Wcat), st)
-        _lib.call("ecb200_point_gemm", _ptr(x), _ptr(Wcat), B, C, N, 2 * Co, _ptr(Y), st)
+        if xhi is not None and xlo is not None and point_gemm_uses_tensor_cores(C):
+            # the per-point GEMM on the tensor cores, from the operands the kNN already made
+            wsplit = torch.empty(2, 2 * Co, C, **f32)
+            _lib.call("ecb200_split_rows_tf32", _ptr(Wcat), 2 * Co * C, _ptr(wsplit[0]), _ptr(wsplit[1]), st)
+            _lib.call("ecb200_point_gemm_tc", _ptr(xhi), _ptr(xlo), _ptr(wsplit[0]), _ptr(wsplit[1]), M, C,
+                      2 * Co, _ptr(Y), st)
+        else:
+            _lib.call("ecb200_point_gemm", _ptr(x), _ptr(Wcat), B, C, N, 2 * Co, _ptr(Y), st)
         _lib.call("ecb200_edge_gather", _ptr(Y), _ptr(idx), _ptr(gamma_c), B, N, k, Co, _ptr(sel),
                   _ptr(arg), _ptr(esum), _ptr(stats) if use_batch_stats else None, st)
         if use_batch_stats and group:
@@ -241,7 +285,7 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
 
 @edgeconv_fwd_op.register_fake
 def _(x, idx, weight, gamma, beta, running_mean, running_var, use_batch_stats, eps, slope,
-      subtract_center, group, save_for_bwd):
+      subtract_center, group, save_for_bwd, xhi, xlo):
     B, C, N = x.shape
     Co = weight.shape[0]
     M = B * N
@@ -313,7 +357,7 @@ def _(gout, x, idx, sel, arg, esum, Y, Wcat, affine, stats, use_batch_stats, slo
 
 def _ec_setup(ctx, inputs, output):
     (x, idx, weight, gamma, beta, _rm, _rv, use_batch_stats, _eps, slope, subtract_center, group,
-     save_for_bwd) = inputs
+     save_for_bwd, _xhi, _xlo) = inputs
     out, sel, arg, esum, Y, Wcat, affine, stats = output
     if not save_for_bwd:
         raise RuntimeError("edgeconv_b200: forward ran with save_for_bwd=False but a gradient "
@@ -326,7 +370,7 @@ def _ec_setup(ctx, inputs, output):
 
 def _ec_backward(ctx, grads):
     gout = grads[0]
-    n_in = 13
+    n_in = 15
     if gout is None:
         return (None,) * n_in
     x, idx, sel, arg, esum, Y, Wcat, affine, stats = ctx.saved_tensors
@@ -352,11 +396,16 @@ def bn_update_running_op(stats: Tensor, running_mean: Optional[Tensor], running_
                   _ptr(running_var), _ptr(num_batches_tracked), _stream(stats))
 
 
+def point_gemm_uses_tensor_cores(C: int) -> bool:
+    """ECB200_GEMM=fma forces the FP32-FMA GEMM (A/B tests)."""
+    return os.environ.get("ECB200_GEMM", "auto") != "fma" and C % 32 == 0 and 32 <= C <= 128
+
+
 def edgeconv(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor,
              running_mean: Optional[Tensor], running_var: Optional[Tensor],
              num_batches_tracked: Optional[Tensor], training: bool, momentum: Optional[float] = 0.1,
              eps: float = 1e-5, slope: float = 0.2, subtract_center: bool = False,
-             group: int = 0) -> Tensor:
+             group: int = 0, xhi: Optional[Tensor] = None, xlo: Optional[Tensor] = None) -> Tensor:
     """Fused EdgeConv block on a given kNN graph:
     max_k LeakyReLU(BatchNorm2d(Conv2d_1x1([x_j (- x_i) ; x_i])))  ->  [B, Co, N]
     (models/dgcnn.py:84-86 with :54-58).  BatchNorm semantics follow nn.BatchNorm2d:
@@ -367,7 +416,8 @@ def edgeconv(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor
         t is not None and t.requires_grad for t in (x, weight, gamma, beta))
     mom = -1.0 if momentum is None else float(momentum)
     res = edgeconv_fwd_op(x, idx, weight, gamma, beta, running_mean, running_var, use_batch_stats,
-                          float(eps), float(slope), bool(subtract_center), int(group), bool(need_grad))
+                          float(eps), float(slope), bool(subtract_center), int(group), bool(need_grad),
+                          xhi, xlo)
     if update_running:
         bn_update_running_op(res[-1].detach(), running_mean, running_var, num_batches_tracked, mom)
     return res[0]

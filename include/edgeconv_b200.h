@@ -94,6 +94,9 @@ int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, int B, int 
                   void* stream);
 int ecb200_debug_tc_scores(const float* hi, const float* lo, const float* xx, int B, int C, int N,
                            float* scores, void* stream);
+/* hi = tf32(src), lo = tf32(src - hi), element-wise over n values (operand prep for the
+ * tensor-core GEMM: Wcat is already K-major) */
+int ecb200_split_rows_tf32(const float* src, long long n, float* hi, float* lo, void* stream);
 /* diagnostic: ecb200_knn_tc with CTA (0,0) stamping clock64() into timeline[6*256] (int64) */
 int ecb200_debug_tc_timeline(const float* hi, const float* lo, const float* xx, int B, int C, int N,
                              int k, int32_t* idx, void* workspace, long long* timeline, void* stream);
@@ -117,6 +120,12 @@ int ecb200_pack_weight(const float* W, int Co, int C, int subtract_center, float
  * GEMM that replaces the k-fold 1x1 convolution over [B,2C,N,k]. */
 int ecb200_point_gemm(const float* x, const float* Wcat, int B, int C, int N, int Co2,
                       float* Y, void* stream);
+/* The same GEMM on the tensor cores (tcgen05 kind::tf32, 3xTF32, TMA-fed, TMEM accumulators;
+ * the pipeline of ecb200_knn_tc with a dense-store epilogue) from the point-major hi/lo
+ * operands the kNN of the same layer already needs: xhi/xlo [M,C], whi/wlo [2Co,C].
+ * C a multiple of 32 in [32,128]. */
+int ecb200_point_gemm_tc(const float* xhi, const float* xlo, const float* whi, const float* wlo,
+                         long long M, int C, int Co2, float* Y, void* stream);
 
 /* For every point i and channel o, over its k neighbours j: e = U[idx[i,j],o] + V[i,o];
  *   sel[i,o]  = max_j e if gamma[o] >= 0 else min_j e       (what survives BN+LeakyReLU+max)

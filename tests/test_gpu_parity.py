@@ -214,6 +214,41 @@ def test_block_vs_oracle(ec, B, C, N, k, Co, sub, training):
     assert_rel(rvg, rvr, rel=1e-5, what="running_var")
 
 
+@pytest.mark.parametrize("B,C,N,k,Co", [(2, 64, 1024, 20, 64), (2, 64, 300, 20, 128), (1, 128, 1024, 20, 256),
+                                        (2, 32, 200, 8, 24), (1, 96, 128, 40, 64)])
+def test_block_tensor_core_path_vs_oracle(ec, B, C, N, k, Co):
+    """edgeconv_block() on a feature-space layer: tcgen05 kNN + tcgen05 per-point GEMM (3xTF32),
+    against the oracle on the graph the kernel chose, plus that graph against the oracle's."""
+    gen = torch.Generator().manual_seed(C * 7 + N + Co)
+    x = orc.synthetic_features(B, C, N, seed=C + N)
+    block = torch.nn.Sequential(torch.nn.Conv2d(2 * C, Co, 1, bias=False), torch.nn.BatchNorm2d(Co),
+                                torch.nn.LeakyReLU(0.2))
+    with torch.no_grad():
+        block[1].weight.copy_(torch.randn(Co, generator=gen) * 0.5 + 1.0)
+        block[1].weight[::3] *= -1.0
+        block[1].bias.copy_(torch.randn(Co, generator=gen) * 0.3)
+    ref_block = torch.nn.Sequential(torch.nn.Conv2d(2 * C, Co, 1, bias=False), torch.nn.BatchNorm2d(Co),
+                                    torch.nn.LeakyReLU(0.2))
+    ref_block.load_state_dict(block.state_dict())
+    block = block.to(dev()).train()
+    ref_block.train()
+    gout = torch.randn(B, Co, N, generator=gen)
+    xg = x.to(dev()).requires_grad_(True)
+    y, idx = ec.edgeconv_block(xg, block, k)
+    (y * gout.to(dev())).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    yr = ref_block(orc.graph_feature_oracle(xr, k, idx=idx.long().cpu())).max(-1)[0]
+    (yr * gout).sum().backward()
+    assert_rel(y, yr, what="out")
+    assert_rel(xg.grad, xr.grad, what="dx")
+    assert_rel(block[0].weight.grad, ref_block[0].weight.grad, what="dW")
+    assert_rel(block[1].weight.grad, ref_block[1].weight.grad, what="dgamma")
+    assert_rel(block[1].bias.grad, ref_block[1].bias.grad, what="dbeta")
+    assert_rel(block[1].running_var, ref_block[1].running_var, rel=1e-5, what="running_var")
+    rep = orc.knn_mismatch_report(x, idx.cpu(), orc.knn_oracle(x, k), rel_eps=TIE_EPS)
+    assert rep["bad_rows"] == 0, rep
+
+
 def test_block_no_grad_and_inference_mode(ec):
     g = load_golden("block_B3_C6_N80_k7_Co16.npz")
     d = dev()
