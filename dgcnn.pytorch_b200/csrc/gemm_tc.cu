@@ -1,0 +1,312 @@
+// Backward GEMMs of the split edge MLP on the tensor cores (tcgen05 kind::tf32, 3xTF32).
+//
+//   gemm_dx : dx[B,C,N]    = dY[M,2Co] . Wcat[2Co,C]      K = 2Co (up to 512): both operands are
+//             streamed K-block by K-block through a TMA / mbarrier ring (K-major tiles),
+//             the result is written straight back in the reference's channel-major layout.
+//   gemm_dw : dWcat[2Co,C] = dY^T . X                      K = M = B*N points: the reduction runs
+//             over the ROWS of the point-major arrays, so both operands are consumed as
+//             MN-major tiles (no transposed copies); the M-long reduction is cut into slabs
+//             over CTAs and the partial 128 x C tiles are reduced with fp32 atomics.
+//
+// Operands are the tf32 hi/lo halves of the fp32 values (ecb200_split_rows_tf32 /
+// ecb200_split_tf32); D += Ahi.Bhi + Ahi.Blo + Alo.Bhi accumulates in TMEM in FP32.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2-5 = epilogue (tcgen05.ld, lane = output row).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+using namespace ecb200::tc;
+
+constexpr int BM = 128;                   // output rows per CTA (= TMEM lanes)
+constexpr int KB = 32;                    // K elements per stage
+constexpr int SUB = BM * KB * 4;          // 16 KB: one operand half for 128 rows x 32 k
+constexpr int STAGES = 3;
+constexpr int NT = 64 + 128;
+constexpr uint32_t TMEM_COLS = 128;
+constexpr int UMMA_K = 8;
+
+struct Tail {
+  uint64_t full[STAGES], empty[STAGES], done;
+  uint32_t tmem_slot;
+};
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * 4 * SUB + sizeof(Tail);
+
+// MN-major SWIZZLE_128B operand: atoms of 8 K-rows x 128 bytes (32 MN elements); consecutive
+// MN atoms are `lbo` bytes apart, consecutive K atoms 1024 bytes.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_major(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct EpiDx {  // D[m, c] -> dx[b, c, n]   (m = b*N + n)
+  float* dx; int C, N; long long M;
+};
+struct EpiDw {  // D[o, c] += into dWcat[o, c]
+  float* dW; int C, rows;
+};
+
+// MN_MAJOR = false: A[M rows, K] and B[BN rows, K], K contiguous (TMA box 32 k x 128 rows).
+// MN_MAJOR = true : A[K rows, M'] and B[K rows, BN], rows = reduction index (TMA box 32 cols x
+//                   32 rows per 32-column atom).
+template <bool MN_MAJOR, class Epi>
+__global__ void __launch_bounds__(NT, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__ CUtensorMap a_lo,
+               const __grid_constant__ CUtensorMap b_hi, const __grid_constant__ CUtensorMap b_lo,
+               int BN, long long K, long long kslab, Epi epi) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  Tail* T = reinterpret_cast<Tail*>(base + (size_t)STAGES * 4 * SUB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;                     // 128-row tile of the output
+  const long long k_beg = (long long)blockIdx.y * kslab;
+  const long long k_end = k_beg + kslab < K ? k_beg + kslab : K;
+  const int nkb = (int)((k_end - k_beg + KB - 1) / KB);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&a_hi); prefetch_tensormap(&a_lo);
+    prefetch_tensormap(&b_hi); prefetch_tensormap(&b_lo);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&T->full[s], 1); mbar_init(&T->empty[s], 1); }
+    mbar_init(&T->done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(&T->tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = T->tmem_slot;
+  const uint32_t b_bytes = (uint32_t)(BN * KB * 4);  // one half of the B stage
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&T->empty[stage], phase ^ 1);
+        unsigned char* st = base + (size_t)stage * 4 * SUB;  // [A hi | A lo | B hi | B lo]
+        mbar_expect_tx(&T->full[stage], 2 * SUB + 2 * b_bytes);
+        const int k0 = (int)(k_beg + (long long)kb * KB);
+        if (!MN_MAJOR) {
+          tma_load_2d(st, &a_hi, &T->full[stage], k0, mt * BM);
+          tma_load_2d(st + SUB, &a_lo, &T->full[stage], k0, mt * BM);
+          tma_load_2d(st + 2 * SUB, &b_hi, &T->full[stage], k0, 0);
+          tma_load_2d(st + 3 * SUB, &b_lo, &T->full[stage], k0, 0);
+        } else {
+          // one box per 32-column atom: 32 columns x 32 reduction rows = 4 KB
+          for (int a = 0; a < BM / 32; ++a) {
+            tma_load_2d(st + a * 4096, &a_hi, &T->full[stage], mt * BM + a * 32, k0);
+            tma_load_2d(st + SUB + a * 4096, &a_lo, &T->full[stage], mt * BM + a * 32, k0);
+          }
+          for (int a = 0; a < BN / 32; ++a) {
+            tma_load_2d(st + 2 * SUB + a * 4096, &b_hi, &T->full[stage], a * 32, k0);
+            tma_load_2d(st + 3 * SUB + a * 4096, &b_lo, &T->full[stage], a * 32, k0);
+          }
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32_major(BM, BN, MN_MAJOR, MN_MAJOR);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&T->full[stage], phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(base + (size_t)stage * 4 * SUB);
+#pragma unroll
+        for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
+          uint64_t dah, dal, dbh, dbl;
+          if (!MN_MAJOR) {
+            const uint32_t ko = (uint32_t)(k8 * UMMA_K * 4);  // 32 bytes inside the swizzle row
+            dah = make_sw128_kmajor_desc(st + ko);
+            dal = make_sw128_kmajor_desc(st + SUB + ko);
+            dbh = make_sw128_kmajor_desc(st + 2 * SUB + ko);
+            dbl = make_sw128_kmajor_desc(st + 3 * SUB + ko);
+          } else {
+            const uint32_t ko = (uint32_t)(k8 * 1024);  // next 8-row K atom
+            dah = make_sw128_mnmajor_desc(st + ko, 4096);
+            dal = make_sw128_mnmajor_desc(st + SUB + ko, 4096);
+            dbh = make_sw128_mnmajor_desc(st + 2 * SUB + ko, 4096);
+            dbl = make_sw128_mnmajor_desc(st + 3 * SUB + ko, 4096);
+          }
+          mma_tf32(tmem_base, dah, dbh, idesc, (kb | k8) != 0);
+          mma_tf32(tmem_base, dah, dbl, idesc, 1);
+          mma_tf32(tmem_base, dal, dbh, idesc, 1);
+        }
+        mma_commit(&T->empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(&T->done);
+    }
+  } else {
+    // ===================== epilogue (thread = output row) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row inside the tile
+    if (nkb > 0) {
+      mbar_wait(&T->done, 0);
+      tc_fence_after();
+      for (int c4 = 0; c4 < BN / 32; ++c4) {
+        float v[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c4 * 32), v);
+        epi.store(mt * BM + r, c4 * 32, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+struct EpiDxImpl : EpiDx {
+  __device__ __forceinline__ void store(long long m, int c0, const float (&v)[32]) const {
+    if (m >= M) return;
+    const long long b = m / N;
+    const int n = (int)(m - b * N);
+    float* o = dx + ((size_t)b * C + c0) * N + n;  // lanes = consecutive points: coalesced per channel
+#pragma unroll
+    for (int u = 0; u < 32; ++u)
+      if (c0 + u < C) o[(size_t)u * N] = v[u];
+  }
+};
+struct EpiDwImpl : EpiDw {
+  __device__ __forceinline__ void store(long long o, int c0, const float (&v)[32]) const {
+    if (o >= rows) return;
+    float* p = dW + (size_t)o * C + c0;
+#pragma unroll
+    for (int u = 0; u < 32; ++u)
+      if (c0 + u < C) atomicAdd(p + u, v[u]);
+  }
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// row-major [rows, cols] fp32, box = box_cols x box_rows, 128-byte swizzle, zero fill outside
+int make_map(CUtensorMap* m, const float* p, long long rows, long long cols, int box_cols, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    ecb200::set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return ECB200_ERR_CUDA;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ecb200::set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return ECB200_ERR_CUDA;
+  }
+  return ECB200_OK;
+}
+
+template <class K>
+int opt_in_smem(K kern, bool (&seen)[ecb200::kMaxDevices]) {
+  if (ecb200::first_use_on_device(seen))
+    ECB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  return ECB200_OK;
+}
+
+__global__ void transpose_split_kernel(const float* __restrict__ W, int R, int C, float* __restrict__ hiT,
+                                       float* __restrict__ loT) {
+  // W [R, C] row-major -> hiT/loT [C, R] (tf32 halves): tiny (Wcat), one thread per element
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= R * C) return;
+  const int c = e / R, r = e % R;
+  const float v = W[(size_t)r * C + c];
+  const float h = to_tf32(v);
+  hiT[e] = h;
+  loT[e] = to_tf32(v - h);
+}
+
+}  // namespace
+
+extern "C" int ecb200_transpose_split_tf32(const float* W, int R, int C, float* hiT, float* loT,
+                                           void* stream) {
+  ECB_REQUIRE(W && hiT && loT && R >= 1 && C >= 1, "ecb200_transpose_split_tf32: bad arguments");
+  transpose_split_kernel<<<ecb200::ceil_div(R * C, 256), 256, 0, (cudaStream_t)stream>>>(W, R, C, hiT, loT);
+  ECB_LAUNCH_CHECK("transpose_split_kernel");
+  return ECB200_OK;
+}
+
+extern "C" int ecb200_gemm_dx_tc(const float* dYhi, const float* dYlo, const float* WTh, const float* WTl,
+                                 int B, int C, int N, int Co2, float* dx, void* stream) {
+  ECB_REQUIRE(dYhi && dYlo && WTh && WTl && dx, "ecb200_gemm_dx_tc: null pointer");
+  ECB_REQUIRE(B >= 1 && N >= 1, "ecb200_gemm_dx_tc: bad shape");
+  ECB_REQUIRE((C == 32 || C == 64 || C == 128) && Co2 % KB == 0,
+              "ecb200_gemm_dx_tc: needs C in {32,64,128} and 2Co a multiple of 32 (C=%d 2Co=%d)", C, Co2);
+  const long long M = (long long)B * N;
+  CUtensorMap ah, al, bh, bl;
+  int rc;
+  if ((rc = make_map(&ah, dYhi, M, Co2, KB, BM))) return rc;
+  if ((rc = make_map(&al, dYlo, M, Co2, KB, BM))) return rc;
+  if ((rc = make_map(&bh, WTh, C, Co2, KB, C))) return rc;   // B = Wcat^T [C, 2Co], K contiguous
+  if ((rc = make_map(&bl, WTl, C, Co2, KB, C))) return rc;
+  auto kern = gemm_tc_kernel<false, EpiDxImpl>;
+  static thread_local bool seen[ecb200::kMaxDevices] = {};
+  if ((rc = opt_in_smem(kern, seen))) return rc;
+  EpiDxImpl epi;
+  epi.dx = dx; epi.C = C; epi.N = N; epi.M = M;
+  dim3 grid((unsigned)ecb200::ceil_div64(M, BM), 1);
+  kern<<<grid, NT, SMEM_BYTES, (cudaStream_t)stream>>>(ah, al, bh, bl, C, (long long)Co2, (long long)Co2, epi);
+  ECB_LAUNCH_CHECK("gemm_tc_kernel<dx>");
+  return ECB200_OK;
+}
+
+extern "C" int ecb200_gemm_dw_tc(const float* dYhi, const float* dYlo, const float* xhi, const float* xlo,
+                                 long long M, int C, int Co2, float* dWcat, void* stream) {
+  ECB_REQUIRE(dYhi && dYlo && xhi && xlo && dWcat, "ecb200_gemm_dw_tc: null pointer");
+  ECB_REQUIRE(M >= 1, "ecb200_gemm_dw_tc: bad shape");
+  ECB_REQUIRE((C == 32 || C == 64 || C == 128) && Co2 % 32 == 0,
+              "ecb200_gemm_dw_tc: needs C in {32,64,128} and 2Co a multiple of 32 (C=%d 2Co=%d)", C, Co2);
+  cudaStream_t st = (cudaStream_t)stream;
+  ECB_CUDA(cudaMemsetAsync(dWcat, 0, sizeof(float) * (size_t)Co2 * C, st));
+  CUtensorMap ah, al, bh, bl;
+  int rc;
+  // MN-major operands: A = dY [K = M rows, 2Co cols], B = X [K = M rows, C cols]; box 32 cols x 32 rows
+  if ((rc = make_map(&ah, dYhi, M, Co2, 32, KB))) return rc;
+  if ((rc = make_map(&al, dYlo, M, Co2, 32, KB))) return rc;
+  if ((rc = make_map(&bh, xhi, M, C, 32, KB))) return rc;
+  if ((rc = make_map(&bl, xlo, M, C, 32, KB))) return rc;
+  auto kern = gemm_tc_kernel<true, EpiDwImpl>;
+  static thread_local bool seen[ecb200::kMaxDevices] = {};
+  if ((rc = opt_in_smem(kern, seen))) return rc;
+  const int mtiles = ecb200::ceil_div(Co2, BM);
+  long long slabs = (ecb200::kNumSMs + mtiles - 1) / mtiles;      // about one CTA per SM
+  long long kslab = ecb200::ceil_div64(ecb200::ceil_div64(M, slabs), KB) * KB;
+  slabs = ecb200::ceil_div64(M, kslab);
+  EpiDwImpl epi;
+  epi.dW = dWcat; epi.C = C; epi.rows = Co2;
+  dim3 grid(mtiles, (unsigned)slabs);
+  kern<<<grid, NT, SMEM_BYTES, st>>>(ah, al, bh, bl, C, M, kslab, epi);
+  ECB_LAUNCH_CHECK("gemm_tc_kernel<dw>");
+  return ECB200_OK;
+}
