@@ -41,6 +41,9 @@ SIGNATURES = {
     "ecb200_gemm_dx": (P, P, I, I, I, I, P, P),
     "ecb200_gemm_dw": (P, P, I, I, I, I, P, P),
     "ecb200_unpack_weight_grad": (P, I, I, I, P, P),
+    "ecb200_transpose_split_tf32": (P, I, I, P, P, P),
+    "ecb200_gemm_dx_tc": (P, P, P, P, I, I, I, I, P, P),
+    "ecb200_gemm_dw_tc": (P, P, P, P, LL, I, I, P, P),
 }
 
 # kernels each entry point enqueues (memsets are not counted)

@@ -35,15 +35,18 @@ struct Tail {
 };
 constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * 4 * SUB + sizeof(Tail);
 
-// MN-major SWIZZLE_128B operand: atoms of 8 K-rows x 128 bytes (32 MN elements); consecutive
-// MN atoms are `lbo` bytes apart, consecutive K atoms 1024 bytes.
+// MN-major tf32 operand.  For 4-byte types the tensor core only takes MN-major tiles in the
+// "128-byte swizzle with 32-byte atomicity" layout (descriptor layout type 1; TMA
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 4 K-rows x 128 bytes (32 MN elements), the
+// 32-byte chunks of a row XOR-ed with (row & 3).  Consecutive MN atoms are `lbo` bytes apart,
+// consecutive K atoms 512 bytes; one kind::tf32 instruction (K = 8) spans two K atoms.
 __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)(lbo >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)(512 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;   // SWIZZLE_128B_BASE32B
   return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc_tf32_major(int M, int N, int a_mn, int b_mn) {
@@ -208,7 +211,8 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 // row-major [rows, cols] fp32, box = box_cols x box_rows, 128-byte swizzle, zero fill outside
-int make_map(CUtensorMap* m, const float* p, long long rows, long long cols, int box_cols, int box_rows) {
+int make_map(CUtensorMap* m, const float* p, long long rows, long long cols, int box_cols, int box_rows,
+             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
     ecb200::set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -219,7 +223,7 @@ int make_map(CUtensorMap* m, const float* p, long long rows, long long cols, int
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     ecb200::set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -292,10 +296,10 @@ extern "C" int ecb200_gemm_dw_tc(const float* dYhi, const float* dYlo, const flo
   CUtensorMap ah, al, bh, bl;
   int rc;
   // MN-major operands: A = dY [K = M rows, 2Co cols], B = X [K = M rows, C cols]; box 32 cols x 32 rows
-  if ((rc = make_map(&ah, dYhi, M, Co2, 32, KB))) return rc;
-  if ((rc = make_map(&al, dYlo, M, Co2, 32, KB))) return rc;
-  if ((rc = make_map(&bh, xhi, M, C, 32, KB))) return rc;
-  if ((rc = make_map(&bl, xlo, M, C, 32, KB))) return rc;
+  if ((rc = make_map(&ah, dYhi, M, Co2, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_map(&al, dYlo, M, Co2, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_map(&bh, xhi, M, C, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_map(&bl, xlo, M, C, 32, KB, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   auto kern = gemm_tc_kernel<true, EpiDwImpl>;
   static thread_local bool seen[ecb200::kMaxDevices] = {};
   if ((rc = opt_in_smem(kern, seen))) return rc;

@@ -298,7 +298,8 @@ def _(x, idx, weight, gamma, beta, running_mean, running_var, use_batch_stats, e
 @torch.library.custom_op("edgeconv_b200::edgeconv_bwd", mutates_args=(), device_types="cuda")
 def edgeconv_bwd_op(gout: Tensor, x: Tensor, idx: Tensor, sel: Tensor, arg: Tensor, esum: Tensor,
                     Y: Tensor, Wcat: Tensor, affine: Tensor, stats: Tensor, use_batch_stats: bool,
-                    slope: float, subtract_center: bool, group: int) -> List[Tensor]:
+                    slope: float, subtract_center: bool, group: int, xhi: Optional[Tensor],
+                    xlo: Optional[Tensor]) -> List[Tensor]:
     """-> [dx [B,C,N], dW [Co,2C], dgamma [Co], dbeta [Co]]"""
     B, C, N = x.shape
     k = idx.shape[-1]
@@ -340,15 +341,26 @@ def edgeconv_bwd_op(gout: Tensor, x: Tensor, idx: Tensor, sel: Tensor, arg: Tens
         dx = torch.empty(B, C, N, **f32)
         dWcat = torch.empty(2 * Co, C, **f32)
         dW = torch.empty(Co, 2 * C, **f32)
-        _lib.call("ecb200_gemm_dx", _ptr(dY), _ptr(Wcat), B, C, N, 2 * Co, _ptr(dx), st)
-        _lib.call("ecb200_gemm_dw", _ptr(dY), _ptr(x), B, C, N, 2 * Co, _ptr(dWcat), st)
+        if xhi is not None and xlo is not None and bwd_gemm_uses_tensor_cores(C, Co):
+            # both backward GEMMs on the tensor cores (3xTF32) from tf32 hi/lo halves
+            dYs = torch.empty(2, M, 2 * Co, **f32)
+            wT = torch.empty(2, C, 2 * Co, **f32)
+            _lib.call("ecb200_split_rows_tf32", _ptr(dY), M * 2 * Co, _ptr(dYs[0]), _ptr(dYs[1]), st)
+            _lib.call("ecb200_transpose_split_tf32", _ptr(Wcat), 2 * Co, C, _ptr(wT[0]), _ptr(wT[1]), st)
+            _lib.call("ecb200_gemm_dx_tc", _ptr(dYs[0]), _ptr(dYs[1]), _ptr(wT[0]), _ptr(wT[1]), B, C, N,
+                      2 * Co, _ptr(dx), st)
+            _lib.call("ecb200_gemm_dw_tc", _ptr(dYs[0]), _ptr(dYs[1]), _ptr(xhi), _ptr(xlo), M, C, 2 * Co,
+                      _ptr(dWcat), st)
+        else:
+            _lib.call("ecb200_gemm_dx", _ptr(dY), _ptr(Wcat), B, C, N, 2 * Co, _ptr(dx), st)
+            _lib.call("ecb200_gemm_dw", _ptr(dY), _ptr(x), B, C, N, 2 * Co, _ptr(dWcat), st)
         _lib.call("ecb200_unpack_weight_grad", _ptr(dWcat), Co, C, int(subtract_center), _ptr(dW), st)
     return [dx, dW, dgamma, dbeta]
 
 
 @edgeconv_bwd_op.register_fake
 def _(gout, x, idx, sel, arg, esum, Y, Wcat, affine, stats, use_batch_stats, slope,
-      subtract_center, group):
+      subtract_center, group, xhi, xlo):
     B, C, N = x.shape
     Co = sel.shape[1]
     f = x.new_empty
@@ -362,7 +374,7 @@ def _ec_setup(ctx, inputs, output):
     if not save_for_bwd:
         raise RuntimeError("edgeconv_b200: forward ran with save_for_bwd=False but a gradient "
                            "is required")
-    ctx.save_for_backward(x, idx, sel, arg, esum, Y, Wcat, affine, stats)
+    ctx.save_for_backward(x, idx, sel, arg, esum, Y, Wcat, affine, stats, _xhi, _xlo)
     ctx.cfg = (use_batch_stats, slope, subtract_center, group)
     ctx.wshape = tuple(weight.shape)
     ctx.set_materialize_grads(False)
@@ -373,10 +385,10 @@ def _ec_backward(ctx, grads):
     n_in = 15
     if gout is None:
         return (None,) * n_in
-    x, idx, sel, arg, esum, Y, Wcat, affine, stats = ctx.saved_tensors
+    x, idx, sel, arg, esum, Y, Wcat, affine, stats, xhi, xlo = ctx.saved_tensors
     use_batch_stats, slope, subtract_center, group = ctx.cfg
     dx, dW, dgamma, dbeta = edgeconv_bwd_op(gout, x, idx, sel, arg, esum, Y, Wcat, affine, stats,
-                                            use_batch_stats, slope, subtract_center, group)
+                                            use_batch_stats, slope, subtract_center, group, xhi, xlo)
     return (dx, None, dW.view(ctx.wshape), dgamma, dbeta) + (None,) * (n_in - 5)
 
 
@@ -399,6 +411,11 @@ def bn_update_running_op(stats: Tensor, running_mean: Optional[Tensor], running_
 def point_gemm_uses_tensor_cores(C: int) -> bool:
     """ECB200_GEMM=fma forces the FP32-FMA GEMM (A/B tests)."""
     return os.environ.get("ECB200_GEMM", "auto") != "fma" and C % 32 == 0 and 32 <= C <= 128
+
+
+def bwd_gemm_uses_tensor_cores(C: int, Co: int) -> bool:
+    return (os.environ.get("ECB200_GEMM", "auto") != "fma" and C in (32, 64, 128)
+            and (2 * Co) % 32 == 0)
 
 
 def edgeconv(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor,

@@ -198,6 +198,20 @@ int ecb200_gemm_dx(const float* dY, const float* Wcat, int B, int C, int N, int 
                    void* stream);
 int ecb200_gemm_dw(const float* dY, const float* x, int B, int C, int N, int Co2, float* dWcat,
                    void* stream);
+/* The two backward GEMMs on the tensor cores (gemm_tc.cu; tcgen05 kind::tf32, 3xTF32, TMA-fed,
+ * FP32 accumulators in TMEM).  Operands are tf32 hi/lo halves:
+ *   dYhi/dYlo [M,2Co]   = ecb200_split_rows_tf32(dY)
+ *   WTh/WTl   [C,2Co]   = ecb200_transpose_split_tf32(Wcat)   (Wcat^T, K = 2Co contiguous)
+ *   xhi/xlo   [M,C]     = the point-major operands of the forward (ecb200_split_tf32)
+ * gemm_dx_tc streams K = 2Co through a TMA ring and writes dx in the reference's [B,C,N]
+ * layout; gemm_dw_tc reduces over the M points with both operands consumed MN-major (no
+ * transposed copies), slabs of points per CTA, partial tiles combined with fp32 atomics
+ * (callee zero-fills dWcat).  C in {32,64,128}, 2Co a multiple of 32. */
+int ecb200_transpose_split_tf32(const float* W, int R, int C, float* hiT, float* loT, void* stream);
+int ecb200_gemm_dx_tc(const float* dYhi, const float* dYlo, const float* WTh, const float* WTl,
+                      int B, int C, int N, int Co2, float* dx, void* stream);
+int ecb200_gemm_dw_tc(const float* dYhi, const float* dYlo, const float* xhi, const float* xlo,
+                      long long M, int C, int Co2, float* dWcat, void* stream);
 /* dW[Co,2C] from dWcat (inverse of ecb200_pack_weight, including subtract_center) */
 int ecb200_unpack_weight_grad(const float* dWcat, int Co, int C, int subtract_center, float* dW,
                               void* stream);

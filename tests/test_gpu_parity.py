@@ -47,6 +47,28 @@ def assert_rel(ours, ref, rel=REL, what=""):
     assert err <= rel * max(scale, 1e-30), f"{what}: max|diff| {err:.3e} > {rel} * {scale:.3e}"
 
 
+def assert_rel_modulo_arg_flips(ours, ref, group_dim, max_groups, rel=REL, what=""):
+    """Like assert_rel, but tolerant of a few arg-max flips.  Where two neighbours of a point
+    give the same e_ij to within fp32 rounding (|gap| ~ 1e-7 relative), the max over k may pick
+    either; the forward value is the same, but the gradient of that (point, channel) is routed
+    to a different neighbour, which changes dx at two points / dW in one row by O(|g|).  The
+    reference's own max has the same discontinuity.  So: all elements within `rel`, except
+    violations confined to at most `max_groups` slices along `group_dim`."""
+    ours, ref = ours.detach().cpu().double(), ref.detach().cpu().double()
+    assert ours.shape == ref.shape, f"{what}: shape {tuple(ours.shape)} vs {tuple(ref.shape)}"
+    scale = max(ref.abs().max().item(), 1e-30)
+    bad = (ours - ref).abs() > rel * scale
+    if not bad.any():
+        return
+    other = [d for d in range(bad.dim()) if d != group_dim % bad.dim()]
+    groups = int(bad.any(dim=other[0]).sum()) if len(other) == 1 else int(
+        bad.flatten(0, 1).any(dim=0).sum() if group_dim % bad.dim() == 2 else bad.any(dim=other).sum())
+    err = (ours - ref).abs().max().item()
+    assert groups <= max_groups and err <= 0.05 * scale, (
+        f"{what}: max|diff| {err:.3e} vs scale {scale:.3e}; {int(bad.sum())} elements in {groups} "
+        f"slices violate {rel} (more than {max_groups} arg-max flips can explain)")
+
+
 def check_knn(ec, x, k, idx_ref=None):
     idx = ec.knn(x.to(dev()), k)
     assert idx.dtype == torch.int64 and tuple(idx.shape) == (x.shape[0], x.shape[2], k)
@@ -220,6 +242,7 @@ def test_block_tensor_core_path_vs_oracle(ec, B, C, N, k, Co):
     """edgeconv_block() on a feature-space layer: tcgen05 kNN + tcgen05 per-point GEMM (3xTF32),
     against the oracle on the graph the kernel chose, plus that graph against the oracle's."""
     gen = torch.Generator().manual_seed(C * 7 + N + Co)
+    torch.manual_seed(C * 11 + N + Co)             # Conv2d default init draws from the global RNG
     x = orc.synthetic_features(B, C, N, seed=C + N)
     block = torch.nn.Sequential(torch.nn.Conv2d(2 * C, Co, 1, bias=False), torch.nn.BatchNorm2d(Co),
                                 torch.nn.LeakyReLU(0.2))
@@ -240,8 +263,11 @@ def test_block_tensor_core_path_vs_oracle(ec, B, C, N, k, Co):
     yr = ref_block(orc.graph_feature_oracle(xr, k, idx=idx.long().cpu())).max(-1)[0]
     (yr * gout).sum().backward()
     assert_rel(y, yr, what="out")
-    assert_rel(xg.grad, xr.grad, what="dx")
-    assert_rel(block[0].weight.grad, ref_block[0].weight.grad, what="dW")
+    # 3xTF32 rounds U, V differently from the fp32 reference (~1e-6 relative): near-ties of the
+    # max over k may resolve to the other neighbour (see assert_rel_modulo_arg_flips)
+    assert_rel_modulo_arg_flips(xg.grad, xr.grad, group_dim=2, max_groups=8, what="dx")
+    assert_rel_modulo_arg_flips(block[0].weight.grad.flatten(1), ref_block[0].weight.grad.flatten(1),
+                                group_dim=0, max_groups=4, what="dW")
     assert_rel(block[1].weight.grad, ref_block[1].weight.grad, what="dgamma")
     assert_rel(block[1].bias.grad, ref_block[1].bias.grad, what="dbeta")
     assert_rel(block[1].running_var, ref_block[1].running_var, rel=1e-5, what="running_var")
