@@ -60,9 +60,7 @@ def assert_rel_modulo_arg_flips(ours, ref, group_dim, max_groups, rel=REL, what=
     bad = (ours - ref).abs() > rel * scale
     if not bad.any():
         return
-    other = [d for d in range(bad.dim()) if d != group_dim % bad.dim()]
-    groups = int(bad.any(dim=other[0]).sum()) if len(other) == 1 else int(
-        bad.flatten(0, 1).any(dim=0).sum() if group_dim % bad.dim() == 2 else bad.any(dim=other).sum())
+    groups = int(bad.movedim(group_dim, -1).reshape(-1, bad.shape[group_dim]).any(dim=0).sum())
     err = (ours - ref).abs().max().item()
     assert groups <= max_groups and err <= 0.05 * scale, (
         f"{what}: max|diff| {err:.3e} vs scale {scale:.3e}; {int(bad.sum())} elements in {groups} "
