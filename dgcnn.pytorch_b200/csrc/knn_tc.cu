@@ -16,6 +16,8 @@
 #include <cuda.h>
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "topk_select.cuh"
@@ -32,23 +34,24 @@ constexpr int TILE_BYTES = BM * KB * 4;  // 16 KB: one K-block of one operand ha
 constexpr int MAX_KB = 4;                // C <= 128 keeps the query tile resident
 constexpr int NUM_EPI = 128;             // threads per epilogue warpgroup (one per TMEM lane)
 constexpr int NT = 64 + 2 * NUM_EPI;     // producer warp + MMA warp + two epilogue warpgroups
-constexpr uint32_t TMEM_COLS = 2 * BN;   // two accumulator stages
+constexpr uint32_t TMEM_COLS = 512;      // two accumulator stages (2 x 128 columns) + the query tile
+constexpr uint32_t A_COL0 = 2 * BN;      // hi at columns [256, 256+C), lo at [256+C, 256+2C)
+constexpr int NSTAGE = 5;                // B ring: 5 x 32 KB; the final ranking reuses these 160 KB
 constexpr int UMMA_K = 8;                // tf32: 32 bytes of K per instruction
 constexpr int KMAX = 40;                 // largest k this kernel takes
 
 struct SharedTail {  // lives after the operand tiles
   float hx[2][2][BN];          // [group][ping-pong] -0.5*|x_j|^2 of the current column tile
-  float stage_s[16][2 * NUM_EPI];  // pass B: the 16 scores a thread is currently testing
+  float stage_s[16][2 * NUM_EPI];  // exchange of the sorted bins between the two threads of a row
   int cnt_x[2][NUM_EPI];           // survivor-count exchange between the two threads of a row
-  uint64_t a_full, b_full[4], b_empty[4], t_full[2], t_empty[2];
+  float xmax_w[2 * NUM_EPI / 32];  // per-warp max |x_j|^2 over the candidates it staged
+  uint64_t a_full, b_full[NSTAGE], b_empty[NSTAGE], t_full[2], t_empty[2];
   uint32_t tmem_slot;
 };
 
-// operand area = (2*nkb + 2*stages) * 16 KB must stay >= 160 KB: the final ranking reuses it
-__host__ __device__ constexpr int num_stages(int nkb) { return nkb == 1 ? 4 : (nkb == 2 ? 3 : 2); }
-__host__ __device__ constexpr size_t smem_bytes(int nkb) {
-  return 1024 /* alignment slack */ + (size_t)(2 * nkb + 2 * num_stages(nkb)) * TILE_BYTES +
-         sizeof(SharedTail);
+// the B ring (NSTAGE x 32 KB = 160 KB) is reused by the final ranking: cap * 256 keys * 8 bytes
+__host__ __device__ constexpr size_t smem_bytes() {
+  return 1024 /* alignment slack */ + (size_t)(2 * NSTAGE) * TILE_BYTES + sizeof(SharedTail);
 }
 
 template <int NBINS>
@@ -71,6 +74,34 @@ __device__ __forceinline__ void sort_bins_desc(float (&v)[NBINS]) {
   }
 }
 
+// Overflow of a thread's survivor list (only with massive ties or clustered data): keep its own
+// best k keys in place and return the score a later candidate must reach to matter ("strictly
+// better than the k-th kept": later candidates of equal score have a larger j, hence a smaller
+// key).  Out of line and not unrolled: it must not bloat the hot loop's instruction footprint.
+// raw survivor entry (score bits << 32 | j) -> totally ordered key (larger score, then smaller j)
+__device__ __forceinline__ uint64_t ordered_key(uint64_t raw) {
+  return make_key(__uint_as_float((uint32_t)(raw >> 32)), (int)(uint32_t)raw);
+}
+__device__ __noinline__ float shrink_survivors(uint64_t* buf, int cnt, int k) {
+  constexpr int LS = 2 * NUM_EPI;
+#pragma unroll 1
+  while (cnt > k) {
+    int arg = 0;
+    uint64_t mn = ordered_key(buf[0]);
+#pragma unroll 1
+    for (int e = 1; e < cnt; ++e) {
+      const uint64_t w = ordered_key(buf[e * LS]);
+      if (w < mn) { mn = w; arg = e; }
+    }
+    --cnt;
+    buf[arg * LS] = buf[cnt * LS];
+  }
+  uint64_t mn = ordered_key(buf[0]);
+#pragma unroll 1
+  for (int e = 1; e < cnt; ++e) mn = min(mn, ordered_key(buf[e * LS]));
+  return nextafterf(key_score(mn), CUDART_INF_F);
+}
+
 // Optional timeline (diagnostics): CTA (0,0) stamps clock64() into tl[role*256 + i]
 #define ECB_STAMP(role, i)                                                                  \
   do {                                                                                      \
@@ -80,22 +111,23 @@ __device__ __forceinline__ void sort_bins_desc(float (&v)[NBINS]) {
 // DEBUG = true: one sweep, raw scores written to dbg[B,N,N] (validation of the MMA plumbing)
 template <int NBINS, bool DEBUG>
 __global__ void __launch_bounds__(NT, 1)
-knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g,
               const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
               const float* __restrict__ xx, int Na, int N, int nkb, int k,
-              uint64_t* __restrict__ surv_ws, float* __restrict__ exch, int cap,
+              uint64_t* __restrict__ surv_ws, int cap,
               int32_t* __restrict__ idx, float* __restrict__ dbg, long long* tl) {
-  // A operand: rows [b*Na + rt*128, +128) of map_hi/lo (the queries; for the GEMM use the points).
+  // A operand: rows [b*Na + rt*128, +128) of a_hi_g / a_lo_g [*, C] (the queries; for the GEMM use
+  // the points), copied ONCE into tensor memory (lane = row, column = channel): the MMAs then
+  // read only the B operand from shared memory, which halves their shared-memory traffic.
   // B operand: rows [b*N + ct*128, +128) of map_bhi/blo (the candidates; for the GEMM the rows of
-  // Wcat).  kNN passes the same maps twice and Na == N.
+  // Wcat), streamed through a TMA / mbarrier ring.  For kNN A and B are the same arrays, Na == N.
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round-trip
   // would turn every later access into a generic-address load/store)
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  const int S = num_stages(nkb);
-  unsigned char* a_hi = base;                                  // [nkb][16 KB]
-  unsigned char* a_lo = a_hi + (size_t)nkb * TILE_BYTES;       // [nkb][16 KB]
-  unsigned char* b_st = a_lo + (size_t)nkb * TILE_BYTES;       // [S][hi 16 KB | lo 16 KB]
+  constexpr int S = NSTAGE;
+  const int C = nkb * KB;
+  unsigned char* b_st = base;                                  // [S][hi 16 KB | lo 16 KB]
   SharedTail* T = reinterpret_cast<SharedTail*>(b_st + (size_t)S * 2 * TILE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,11 +138,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const int a_row0 = b * Na;      // first global A row of this cloud
 
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&map_hi);
-    prefetch_tensormap(&map_lo);
     prefetch_tensormap(&map_bhi);
     prefetch_tensormap(&map_blo);
-    mbar_init(&T->a_full, 1);
+    mbar_init(&T->a_full, 2 * NUM_EPI);
     for (int s = 0; s < S; ++s) { mbar_init(&T->b_full[s], 1); mbar_init(&T->b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&T->t_full[s], 1); mbar_init(&T->t_empty[s], NUM_EPI); }
     fence_barrier_init();
@@ -121,15 +151,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = T->tmem_slot;
   if (threadIdx.x == 0) ECB_STAMP(5, 0);
+  if (tl && threadIdx.x == 0) {  // diagnostics: wall-clock span and SM of every CTA
+    unsigned long long t; unsigned sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    long long* e = tl + 6 * 256 + 3 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+    e[0] = (long long)t; e[2] = sm;
+  }
 
   if (warp == 0) {
     // ===================== TMA producer (one lane) =====================
     if (lane == 0) {
-      mbar_expect_tx(&T->a_full, (uint32_t)(2 * nkb * TILE_BYTES));
-      for (int kb = 0; kb < nkb; ++kb) {
-        tma_load_2d(a_hi + (size_t)kb * TILE_BYTES, &map_hi, &T->a_full, kb * KB, a_row0 + rt * BM);
-        tma_load_2d(a_lo + (size_t)kb * TILE_BYTES, &map_lo, &T->a_full, kb * KB, a_row0 + rt * BM);
-      }
       int stage = 0;
       uint32_t phase = 0;
       for (int pass = 0; pass < npass; ++pass)
@@ -138,9 +170,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             mbar_wait(&T->b_empty[stage], phase ^ 1);
             ECB_STAMP(0, (pass * nct + ct) * nkb + kb);
             unsigned char* dst = b_st + (size_t)stage * 2 * TILE_BYTES;
-            mbar_expect_tx(&T->b_full[stage], 2 * TILE_BYTES);
+            const bool need_lo = DEBUG || pass == 1;  // pass A multiplies the hi halves only
+            mbar_expect_tx(&T->b_full[stage], need_lo ? 2 * TILE_BYTES : TILE_BYTES);
             tma_load_2d(dst, &map_bhi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
-            tma_load_2d(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+            if (need_lo)
+              tma_load_2d(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
     }
@@ -153,7 +187,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int tile = 0;
-      for (int pass = 0; pass < npass; ++pass)
+      const uint32_t ring_lo = sw128_kmajor_desc_lo(smem_u32(b_st));  // descriptor low word of stage 0, hi half
+      constexpr uint32_t STAGE_STEP = (2 * TILE_BYTES) >> 4, LO_STEP = TILE_BYTES >> 4, K8_STEP = (UMMA_K * 4) >> 4;
+      const uint32_t a_col = tmem_base + A_COL0;
+      for (int pass = 0; pass < npass; ++pass) {
+        const bool three = DEBUG || pass == 1;  // pass A ranks with plain TF32 and an error margin
         for (int ct = 0; ct < nct; ++ct, ++tile) {
           const int as = tile & 1;  // stage g is consumed by epilogue warpgroup g
           mbar_wait(&T->t_empty[as], ((tile >> 1) & 1) ^ 1);  // that group drained this stage
@@ -163,18 +201,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&T->b_full[stage], phase);
             tc_fence_after();
-            const uint32_t ah = smem_u32(a_hi + (size_t)kb * TILE_BYTES);
-            const uint32_t al = smem_u32(a_lo + (size_t)kb * TILE_BYTES);
-            const uint32_t bh = smem_u32(b_st + (size_t)stage * 2 * TILE_BYTES);
-            const uint32_t bl = bh + TILE_BYTES;
+            const uint32_t ah = a_col + (uint32_t)(kb * KB);  // tensor-memory columns of A hi; lo at +C
+            const uint32_t bh = ring_lo + (uint32_t)stage * STAGE_STEP;
+            if (three) {
 #pragma unroll
-            for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
-              const uint32_t ko = (uint32_t)(k8 * UMMA_K * 4);  // byte offset inside the swizzle row
-              const uint64_t dah = make_sw128_kmajor_desc(ah + ko), dal = make_sw128_kmajor_desc(al + ko);
-              const uint64_t dbh = make_sw128_kmajor_desc(bh + ko), dbl = make_sw128_kmajor_desc(bl + ko);
-              mma_tf32(d_tmem, dah, dbh, idesc, (kb | k8) != 0);
-              mma_tf32(d_tmem, dah, dbl, idesc, 1);
-              mma_tf32(d_tmem, dal, dbh, idesc, 1);
+              for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
+                mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, (kb | k8) != 0);
+                mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + LO_STEP + k8 * K8_STEP, idesc, 1);
+                mma_tf32_ts_lo(d_tmem, ah + (uint32_t)C + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, 1);
+              }
+            } else {
+#pragma unroll
+              for (int k8 = 0; k8 < KB / UMMA_K; ++k8)
+                mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, (kb | k8) != 0);
             }
             mma_commit(&T->b_empty[stage]);  // frees the stage once these MMAs have read it
             if (++stage == S) { stage = 0; phase ^= 1; }
@@ -182,6 +221,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           mma_commit(&T->t_full[as]);  // accumulator ready for the epilogue
           ECB_STAMP(1, 2 * tile + 1);
         }
+      }
     }
   } else {
     // ===================== epilogue: selection (thread = query row) =====================
@@ -194,10 +234,30 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     const int row = rt * BM + q * 32 + lane;
     const bool valid = row < Na;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN);
+    {
+      // query rows -> tensor memory: group 0 copies the hi halves, group 1 the lo halves
+      const float* src = (g == 0 ? a_hi_g : a_lo_g) + (size_t)(a_row0 + row) * C;
+      const uint32_t dst = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + (uint32_t)(g * C);
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        uint32_t r[32];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) f = __ldg(reinterpret_cast<const float4*>(src + c0) + e);
+          r[4 * e + 0] = __float_as_uint(f.x); r[4 * e + 1] = __float_as_uint(f.y);
+          r[4 * e + 2] = __float_as_uint(f.z); r[4 * e + 3] = __float_as_uint(f.w);
+        }
+        __syncwarp();
+        tmem_st_32x32(dst + (uint32_t)c0, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&T->a_full);
+    }
     float bin[NBINS];
 #pragma unroll
     for (int u = 0; u < NBINS; ++u) bin[u] = -CUDART_INF_F;
-    // workspace layouts are [tile][slot][group][row-in-tile]: for a fixed slot the 32 lanes of
+    // workspace layout is [tile][slot][group][row-in-tile]: for a fixed slot the 32 lanes of
     // a warp (consecutive rows) touch consecutive words, so the traffic coalesces
     const size_t tile_id = (size_t)b * gridDim.x + rt;
     constexpr int LS = 2 * NUM_EPI;  // stride between a thread's consecutive slots
@@ -205,42 +265,33 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     float* stage_s = &T->stage_s[0][g * NUM_EPI + et];
     int cnt = 0;
     float thr = CUDART_INF_F;
+    float xmax = 0.f;  // max |x_j|^2 over the candidates this thread staged (for the pass-A margin)
     int use = 0;  // how many times this group has consumed its accumulator stage
-    for (int pass = 0; pass < npass; ++pass) {
-      if (pass == 1) {
-        if (et == 0) ECB_STAMP(4, 8 * g + 5);
-        sort_bins_desc<NBINS>(bin);
-        if (et == 0) ECB_STAMP(4, 8 * g + 6);
-        float tau;
-        // The row's two threads pool their bins: the k-th largest of the union of both
-        // sorted lists is  max_i min(mine[i-1], theirs[k-i-1])  (i taken from mine).  The
-        // lists travel through the L2-resident workspace (shared memory is full of tiles).
-        float* myx = exch + tile_id * (size_t)KMAX * LS + g * NUM_EPI + et;
-        const float* ox = exch + tile_id * (size_t)KMAX * LS + (g ^ 1) * NUM_EPI + et;
-#pragma unroll
-        for (int u = 0; u < KMAX; ++u)
-          if (u < k) myx[u * LS] = u < NBINS ? bin[u < NBINS ? u : 0] : -CUDART_INF_F;
-        __threadfence_block();
-        asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
-        tau = -CUDART_INF_F;
-        float theirs[KMAX + 1];
-#pragma unroll
-        for (int i = 0; i <= KMAX; ++i) theirs[i] = __ldcg(ox + max(k - i - 1, 0) * LS);  // independent loads
-#pragma unroll
-        for (int i = 0; i <= KMAX; ++i) {
-          const float mine = i == 0 ? CUDART_INF_F : (i - 1 < NBINS ? bin[i - 1 < NBINS ? i - 1 : 0] : -CUDART_INF_F);
-          const float t = i >= k ? CUDART_INF_F : theirs[i];
-          if (i <= k) tau = fmaxf(tau, fminf(mine, t));
-        }
-        thr = fmaxf(tau, -3.0e38f);  // masked candidates score -inf and must never pass
-        if (et == 0) ECB_STAMP(4, 8 * g + 7);
-      }
+    // |x_j|^2 of column `et` of candidate tile t; -1 marks a column past the end of the cloud
+    auto load_xx = [&](int t) -> float {
+      const int j = t * BN + et;
+      return (xx && j < N) ? __ldg(xx + cloud_row0 + j) : (xx ? -1.f : 0.f);
+    };
+    int xnext_t = g & 1;
+    float xnext = load_xx(xnext_t);
+    // the tile loop of one pass; `pass` is a compile-time constant in each instantiation, so the
+    // two passes get separate code (and register allocations: the bins die after the first)
+    auto run_tiles = [&](auto pass_tag) {
+      constexpr int pass = decltype(pass_tag)::value;
       for (int ct = (pass * nct + g) & 1; ct < nct; ct += 2, ++use) {
         float* hx = T->hx[g][use & 1];
         if (et == 0) ECB_STAMP(2 + g, 4 * use);
         {
-          const int j = ct * BN + et;
-          hx[et] = xx ? ((j < N) ? -0.5f * xx[cloud_row0 + j] : -CUDART_INF_F) : 0.f;
+          // |x_j|^2 of this tile's column was fetched one tile ahead (an L2 round trip off the
+          // critical path); now fetch the next tile's (or the first tile's of the next pass)
+          if (xnext_t != ct) xnext = load_xx(ct);  // only when a pass has no tile for this group
+          const float xj = xnext;
+          int nct_t = ct + 2;
+          if (nct_t >= nct) nct_t = ((pass + 1) * nct + g) & 1;
+          xnext = load_xx(nct_t);
+          xnext_t = nct_t;
+          xmax = fmaxf(xmax, xj);
+          hx[et] = xx ? ((xj >= 0.f) ? -0.5f * xj : -CUDART_INF_F) : 0.f;
         }
         if (g == 0) asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI) : "memory");
         else        asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI) : "memory");
@@ -248,88 +299,154 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         mbar_wait(&T->t_full[g], use & 1);
         tc_fence_after();
         if (et == 0) ECB_STAMP(2 + g, 4 * use + 2);
-#pragma unroll 1
-        for (int c2 = 0; c2 < BN / 64; ++c2) {
+        // one 32-column chunk of this row: add the column term, then store / bin / select
+        auto process = [&](const uint32_t(&cur)[32], const int c4, const bool second_pass) {
+          const float4* hx4 = reinterpret_cast<const float4*>(hx + c4 * 32);
+          float v[32];
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int c4 = c2 * 2 + hf;
-            float v[32];
-            __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned)
-            tmem_ld_32x32(lane_base + (uint32_t)(c4 * 32), v);
-            const float4* hx4 = reinterpret_cast<const float4*>(hx + c4 * 32);
+          for (int e = 0; e < 8; ++e) {
+            const float4 h4 = hx4[e];
+            v[4 * e + 0] = __uint_as_float(cur[4 * e + 0]) + h4.x;
+            v[4 * e + 1] = __uint_as_float(cur[4 * e + 1]) + h4.y;
+            v[4 * e + 2] = __uint_as_float(cur[4 * e + 2]) + h4.z;
+            v[4 * e + 3] = __uint_as_float(cur[4 * e + 3]) + h4.w;
+          }
+          if (DEBUG) {  // dense store of the tile: raw scores, or the GEMM result Y = A.B^T
+            if (valid) {
+              float* orow = dbg + ((size_t)(a_row0 + row)) * N + ct * BN + c4 * 32;
+              if ((N & 3) == 0) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float4 h4 = hx4[e];
-              v[4 * e + 0] += h4.x; v[4 * e + 1] += h4.y; v[4 * e + 2] += h4.z; v[4 * e + 3] += h4.w;
+                for (int e = 0; e < 8; ++e)
+                  if (ct * BN + c4 * 32 + 4 * e < N)
+                    *reinterpret_cast<float4*>(orow + 4 * e) =
+                        make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 32; ++u)
+                  if (ct * BN + c4 * 32 + u < N) orow[u] = v[u];
+              }
             }
-            if (DEBUG) {  // dense store of the tile: raw scores, or the GEMM result Y = A.B^T
-              if (valid) {
-                float* orow = dbg + ((size_t)(a_row0 + row)) * N + ct * BN + c4 * 32;
-                if ((N & 3) == 0) {
+          } else if (!second_pass) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (ct * BN + c4 * 32 + 4 * e < N)
-                      *reinterpret_cast<float4*>(orow + 4 * e) =
-                          make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-                } else {
+            for (int u = 0; u < 32; ++u) {
+              const int bi = (NBINS == 64 ? (c4 & 1) * 32 : 0) + u;
+              bin[bi] = fmaxf(bin[bi], v[u]);
+            }
+          } else {
+            // One ballot per candidate column: the warp branches (uniformly) only for columns
+            // where some row keeps the candidate; those rows append (score bits, j) to their
+            // list in the L2-resident workspace.  Straight-line predicated code: no staging
+            // of the scores, no divergent loops.
+            if (valid && cnt + 32 > cap) {  // rare (ties, clustered data): keep the thread's own best k
+              thr = fmaxf(thr, shrink_survivors(mybuf, cnt, k));
+              cnt = min(cnt, k);
+            }
+            const int jb = ct * BN + c4 * 32;
 #pragma unroll
-                  for (int u = 0; u < 32; ++u)
-                    if (ct * BN + c4 * 32 + u < N) orow[u] = v[u];
-                }
-              }
-            } else if (pass == 0) {
-#pragma unroll
-              for (int u = 0; u < 32; ++u) {
-                const int bi = (NBINS == 64 ? hf * 32 : 0) + u;
-                bin[bi] = fmaxf(bin[bi], v[u]);
-              }
-            } else if (valid) {
-              // 16 candidates at a time: all scores go to the thread's column of a small
-              // shared-memory stage and a 16-bit pass mask is built -- independent, branch-
-              // free work; only rows that actually have a survivor (a few %) then walk
-              // their mask and append keys to the row's list in the L2-resident workspace.
-#pragma unroll
-              for (int h16 = 0; h16 < 2; ++h16) {
-                uint32_t mask = 0;
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                  const float sc = v[h16 * 16 + u];
-                  stage_s[u * (2 * NUM_EPI)] = sc;
-                  mask |= (sc >= thr ? 1u : 0u) << u;
-                }
-                if (mask) {
-                  if (cnt + 16 > cap) {  // slow path: keep this thread's own best k, raise the bar
-                    while (cnt > k) {
-                      int arg = 0;
-                      uint64_t mn = mybuf[0];
-                      for (int e = 1; e < cnt; ++e) {
-                        const uint64_t w = mybuf[e * LS];
-                        if (w < mn) { mn = w; arg = e; }
-                      }
-                      --cnt;
-                      mybuf[arg * LS] = mybuf[cnt * LS];
-                    }
-                    uint64_t mn = mybuf[0];
-                    for (int e = 1; e < cnt; ++e) mn = min(mn, mybuf[e * LS]);
-                    thr = fmaxf(thr, nextafterf(key_score(mn), CUDART_INF_F));
-                  }
-                  const int jb = ct * BN + c4 * 32 + h16 * 16;
-                  while (mask) {
-                    const int u = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const float sc = stage_s[u * (2 * NUM_EPI)];
-                    if (sc >= thr) mybuf[(cnt++) * LS] = make_key(sc, jb + u);  // thr may just have risen
-                  }
+            for (int u = 0; u < 32; ++u) {
+              const bool hit = valid && v[u] >= thr;
+              if (__any_sync(0xffffffffu, hit)) {
+                if (hit) {
+                  mybuf[cnt * LS] = ((uint64_t)__float_as_uint(v[u]) << 32) | (uint32_t)(jb + u);
+                  ++cnt;
                 }
               }
             }
           }
+        };
+        __syncwarp();  // tcgen05.ld / wait are warp-collective (.sync.aligned)
+        if (DEBUG || pass == 0) {
+          // 32 columns at a time, double-buffered: the tcgen05.ld of the next 32 columns is in
+          // flight while the current ones are processed (the bins keep 32 registers busy)
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32_issue(lane_base, ra);
+#pragma unroll
+          for (int c4 = 0; c4 < BN / 32; ++c4) {
+            uint32_t(&cur)[32] = (c4 & 1) ? rb : ra;
+            uint32_t(&nxt)[32] = (c4 & 1) ? ra : rb;
+            tmem_ld_wait(cur);
+            if (c4 + 1 < BN / 32) {
+              tmem_ld_32x32_issue(lane_base + (uint32_t)((c4 + 1) * 32), nxt);
+            } else {
+              tc_fence_before();
+              mbar_arrive(&T->t_empty[g]);  // the whole stage has been read
+            }
+            process(cur, c4, false);
+          }
+        } else {
+          // Second pass: the accumulator row moves into registers as early as the register
+          // budget allows (96 columns, the last 32 as soon as the first chunk is done) and the
+          // stage goes back to the MMA issuer, so the (three times longer) MMAs of this
+          // group's next tile overlap most of the selection instead of waiting for it.
+          uint32_t r0[32], r1[32], r2[32];
+          tmem_ld_32x32_issue(lane_base, r0);
+          tmem_ld_32x32_issue(lane_base + 32u, r1);
+          tmem_ld_32x32_issue(lane_base + 64u, r2);
+          tmem_ld_wait(r0);
+          tmem_ld_wait(r1);
+          tmem_ld_wait(r2);
+          process(r0, 0, true);
+          __syncwarp();
+          tmem_ld_32x32_issue(lane_base + 96u, r0);
+          tmem_ld_wait(r0);
+          tc_fence_before();
+          mbar_arrive(&T->t_empty[g]);
+          process(r1, 1, true);
+          __syncwarp();
+          process(r2, 2, true);
+          __syncwarp();
+          process(r0, 3, true);
         }
-        tc_fence_before();
-        mbar_arrive(&T->t_empty[g]);
         if (et == 0) ECB_STAMP(2 + g, 4 * use + 3);
       }
       if (et == 0) ECB_STAMP(4, 8 * g + pass);
+    };
+    run_tiles(std::integral_constant<int, 0>{});
+    if (!DEBUG) {
+      if (et == 0) ECB_STAMP(4, 8 * g + 5);
+      sort_bins_desc<NBINS>(bin);
+      if (et == 0) ECB_STAMP(4, 8 * g + 6);
+      // The row's two threads pool their bins: the k-th largest of the union of two
+      // descending lists is  max_i min(mine[i-1], theirs[k-i-1])  (i taken from mine).  The
+      // partner's list travels through the (idle between the passes) score staging area of
+      // shared memory, 16 values per round; trev[i] = theirs[k-i-1].
+      const float* other_s = &T->stage_s[0][(g ^ 1) * NUM_EPI + et];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+      if (lane == 0) T->xmax_w[(g * NUM_EPI + et) >> 5] = xmax;  // read after the first bar.sync below
+      float trev[KMAX];
+#pragma unroll
+      for (int i = 0; i < KMAX; ++i) trev[i] = -CUDART_INF_F;  // theirs[>= NBINS] does not exist
+#pragma unroll
+      for (int r = 0; r < NBINS / 16; ++r) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) stage_s[u * LS] = bin[r * 16 + u];
+        asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
+#pragma unroll
+        for (int i = 0; i < KMAX; ++i) {
+          const int t = k - i - 1 - r * 16;
+          if (t >= 0 && t < 16) trev[i] = other_s[t * LS];
+        }
+        asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
+      }
+      float tau = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i <= KMAX; ++i) {
+        const float mine = i == 0 ? CUDART_INF_F : (i - 1 < NBINS ? bin[i - 1 < NBINS ? i - 1 : 0] : -CUDART_INF_F);
+        const float t = i >= k ? CUDART_INF_F : trev[i < KMAX ? i : 0];
+        if (i <= k) tau = fmaxf(tau, fminf(mine, t));
+      }
+      // Pass A scored with the hi.hi product only: |score_A - score_B| <= 2^-11 (|hi_i||x_j| +
+      // |x_i||hi_j|) <= 1.1 * 2^-10 |x_i| max_j|x_j|.  Lowering the bound by that margin keeps
+      // it a lower bound of the row's k-th best 3xTF32 score (a few more survivors, no misses).
+      float cmax = 0.f;
+#pragma unroll
+      for (int w = 0; w < 2 * NUM_EPI / 32; ++w) cmax = fmaxf(cmax, T->xmax_w[w]);
+      const float xi = valid ? xx[cloud_row0 + row] : 0.f;
+      const float margin = 1.1f * 0.0009765625f * sqrtf(xi * cmax) + 1e-30f;
+      thr = fmaxf(tau - margin, -3.0e38f);  // masked candidates score -inf and must never pass
+      if (et == 0) ECB_STAMP(4, 8 * g + 7);
+      run_tiles(std::integral_constant<int, 1>{});
     }
     if (!DEBUG) {
       // Exact top-k of the row's survivors (both groups): rank = number of strictly better
@@ -347,37 +464,43 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         for (int u = 0; u < 8; ++u) tmp[u] = e0 + u < cnt ? __ldcg(mybuf + (e0 + u) * LS) : 0ull;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (e0 + u < cnt) cols[(e0 + u) * (2 * NUM_EPI) + me] = tmp[u];
+          if (e0 + u < cnt) cols[(e0 + u) * (2 * NUM_EPI) + me] = ordered_key(tmp[u]);
       }
       T->cnt_x[g][et] = cnt;
       asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
       if (et == 0) ECB_STAMP(4, 8 * g + 3);
       if (valid) {
-        const int ocnt = T->cnt_x[g ^ 1][et];
+        // The row's two threads split the union of both survivor lists evenly; each ranks its
+        // share against the whole union (keys are distinct, so ranks are a permutation).
+        const int cnt0 = T->cnt_x[0][et], cnt1 = T->cnt_x[1][et];
+        const int total = cnt0 + cnt1;
+        const uint64_t* col0 = cols + et;            // group 0's column, then group 1's
+        const uint64_t* col1 = cols + NUM_EPI + et - (size_t)cnt0 * (2 * NUM_EPI);
+        auto key_at = [&](int f) -> uint64_t {
+          return (f < cnt0 ? col0 : col1)[(size_t)f * (2 * NUM_EPI)];
+        };
         int32_t* out = idx + (size_t)(cloud_row0 + row) * k;
         if (g == 0)
-          for (int p = cnt + ocnt; p < k; ++p) out[p] = N - 1;  // only with NaN input
-        for (int e0 = 0; e0 < cnt; e0 += 8) {  // 8 own keys in registers per sweep of the union
+          for (int p = total; p < k; ++p) out[p] = N - 1;  // only with NaN input
+        const int half = (total + 1) >> 1;
+        const int lo = g * half, hi = min(total, lo + half);
+        for (int e0 = lo; e0 < hi; e0 += 8) {  // 8 keys in registers per sweep of the union
           uint64_t own[8];
           int rank[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            own[u] = e0 + u < cnt ? cols[(e0 + u) * (2 * NUM_EPI) + me] : ~0ull;
+            own[u] = e0 + u < hi ? key_at(e0 + u) : ~0ull;
             rank[u] = 0;
           }
-          for (int f = 0; f < cnt; ++f) {
-            const uint64_t kf = cols[f * (2 * NUM_EPI) + me];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) rank[u] += (kf > own[u]);
-          }
-          for (int f = 0; f < ocnt; ++f) {
-            const uint64_t kf = cols[f * (2 * NUM_EPI) + other];
+#pragma unroll 4
+          for (int f = 0; f < total; ++f) {
+            const uint64_t kf = key_at(f);
 #pragma unroll
             for (int u = 0; u < 8; ++u) rank[u] += (kf > own[u]);
           }
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            if (e0 + u < cnt && rank[u] < k)
+            if (e0 + u < hi && rank[u] < k)
               out[rank[u]] = (int32_t)min(key_index(own[u]), (uint32_t)(N - 1));
         }
       }
@@ -388,6 +511,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (tl && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[6 * 256 + 3 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) + 1] = (long long)t;
+  }
 }
 
 // x[B,C,N] -> point-major hi/lo [M,C] (tf32-rounded halves of the fp32 value) and xx[M]
@@ -478,7 +606,7 @@ int make_operand(OperandMaps* m, const float* hi, const float* lo, long long row
 
 // clouds = grid.y; per cloud Na rows of A (queries / points) and Nb rows of B (candidates / Wcat rows)
 template <int NBINS, bool DEBUG>
-int launch_tc(const OperandMaps& A, const OperandMaps& Bm, const float* xx, int clouds, int C, int Na,
+int launch_tc(const float* a_hi, const float* a_lo, const OperandMaps& Bm, const float* xx, int clouds, int C, int Na,
               int Nb, int k, uint64_t* ws, int cap, int32_t* idx, float* dbg, cudaStream_t st,
               long long* tl = nullptr) {
   const int nkb = C / KB;
@@ -486,12 +614,10 @@ int launch_tc(const OperandMaps& A, const OperandMaps& Bm, const float* xx, int 
   static thread_local bool seen[ecb200::kMaxDevices] = {};
   if (ecb200::first_use_on_device(seen))
     ECB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_bytes(MAX_KB)));
+                                  (int)smem_bytes()));
   dim3 grid(ecb200::ceil_div(Na, BM), clouds);
-  // workspace = survivor keys [tiles][cap][2][128] followed by the bin exchange [tiles][KMAX][2][128]
-  const size_t tiles = (size_t)clouds * ecb200::ceil_div(Na, BM);
-  float* exch = ws ? reinterpret_cast<float*>(ws + tiles * (size_t)cap * 2 * NUM_EPI) : nullptr;
-  kern<<<grid, NT, smem_bytes(nkb), st>>>(A.hi, A.lo, Bm.hi, Bm.lo, xx, Na, Nb, nkb, k, ws, exch, cap, idx,
+  // workspace = survivor keys [tiles][cap][2][128]
+  kern<<<grid, NT, smem_bytes(), st>>>(a_hi, a_lo, Bm.hi, Bm.lo, xx, Na, Nb, nkb, k, ws, cap, idx,
                                           dbg, tl);
   ECB_LAUNCH_CHECK("knn_tc_kernel");
   return ECB200_OK;
@@ -521,13 +647,13 @@ extern "C" int ecb200_split_tf32(const float* x, int B, int C, int N, float* hi,
 
 // survivor slots per (row, epilogue group) in the workspace (2 x 32 pooled bins per row:
 // expected use ~12 per thread at k = 20, ~32 at k = 40; overflow falls back to an exact
-// in-place shrink, so cap >= k + 16).  cap * 256 threads * 8 bytes must fit the >= 160 KB of operand tiles that the
+// in-place shrink before a 32-column chunk, so cap >= k + 32).  cap * 256 threads * 8 bytes must fit the >= 160 KB of operand tiles that the
 // final ranking reuses.
-static int survivor_cap(int k) { return k <= 20 ? 48 : 80; }
+static int survivor_cap(int k) { return k <= 20 ? 56 : 80; }
 
 extern "C" size_t ecb200_knn_tc_workspace_bytes(int B, int N, int k) {
   const size_t tiles = (size_t)B * ecb200::ceil_div(N, BM);
-  return tiles * 2 * NUM_EPI * ((size_t)survivor_cap(k) * sizeof(uint64_t) + KMAX * sizeof(float));
+  return tiles * 2 * NUM_EPI * (size_t)survivor_cap(k) * sizeof(uint64_t);
 }
 
 extern "C" int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, int B, int C, int N,
@@ -546,7 +672,7 @@ extern "C" int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, 
   OperandMaps X;
   int rc = make_operand(&X, hi, lo, (long long)B * N, C);
   if (rc) return rc;
-  return launch_tc<32, false>(X, X, xx, B, C, N, N, k, (uint64_t*)workspace, survivor_cap(k), idx, nullptr,
+  return launch_tc<32, false>(hi, lo, X, xx, B, C, N, N, k, (uint64_t*)workspace, survivor_cap(k), idx, nullptr,
                               (cudaStream_t)stream);
 }
 
@@ -558,7 +684,7 @@ extern "C" int ecb200_debug_tc_timeline(const float* hi, const float* lo, const 
   OperandMaps X;
   int rc = make_operand(&X, hi, lo, (long long)B * N, C);
   if (rc) return rc;
-  return launch_tc<32, false>(X, X, xx, B, C, N, N, k, (uint64_t*)workspace, survivor_cap(k), idx, nullptr,
+  return launch_tc<32, false>(hi, lo, X, xx, B, C, N, N, k, (uint64_t*)workspace, survivor_cap(k), idx, nullptr,
                               (cudaStream_t)stream, timeline);
 }
 
@@ -571,7 +697,7 @@ extern "C" int ecb200_debug_tc_scores(const float* hi, const float* lo, const fl
   OperandMaps X;
   int rc = make_operand(&X, hi, lo, (long long)B * N, C);
   if (rc) return rc;
-  return launch_tc<32, true>(X, X, xx, B, C, N, N, 1, nullptr, 0, nullptr, scores, (cudaStream_t)stream);
+  return launch_tc<32, true>(hi, lo, X, xx, B, C, N, N, 1, nullptr, 0, nullptr, scores, (cudaStream_t)stream);
 }
 
 extern "C" int ecb200_split_rows_tf32(const float* src, long long n, float* hi, float* lo, void* stream) {
@@ -587,11 +713,9 @@ extern "C" int ecb200_point_gemm_tc(const float* xhi, const float* xlo, const fl
   ECB_REQUIRE(M >= 1 && M < (1LL << 31) && Co2 >= 1, "ecb200_point_gemm_tc: bad shape");
   ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB,
               "ecb200_point_gemm_tc: C=%d must be a multiple of 32 in [32, 128]", C);
-  OperandMaps X, W;
-  int rc = make_operand(&X, xhi, xlo, M, C);
-  if (rc) return rc;
-  rc = make_operand(&W, whi, wlo, Co2, C);
+  OperandMaps W;
+  int rc = make_operand(&W, whi, wlo, Co2, C);
   if (rc) return rc;
   // one "cloud": A = all M points, B = the 2Co rows of Wcat, dense store of the tiles into Y[M, 2Co]
-  return launch_tc<32, true>(X, W, nullptr, 1, C, (int)M, Co2, 1, nullptr, 0, nullptr, Y, (cudaStream_t)stream);
+  return launch_tc<32, true>(xhi, xlo, W, nullptr, 1, C, (int)M, Co2, 1, nullptr, 0, nullptr, Y, (cudaStream_t)stream);
 }

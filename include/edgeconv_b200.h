@@ -97,7 +97,9 @@ int ecb200_debug_tc_scores(const float* hi, const float* lo, const float* xx, in
 /* hi = tf32(src), lo = tf32(src - hi), element-wise over n values (operand prep for the
  * tensor-core GEMM: Wcat is already K-major) */
 int ecb200_split_rows_tf32(const float* src, long long n, float* hi, float* lo, void* stream);
-/* diagnostic: ecb200_knn_tc with CTA (0,0) stamping clock64() into timeline[6*256] (int64) */
+/* diagnostic: ecb200_knn_tc with CTA (0,0) stamping clock64() into timeline[0 .. 6*256) and every
+ * CTA its {globaltimer at start, at end, SM id} into timeline[6*256 + 3*cta ..] (int64;
+ * 6*256 + 3*B*ceil(N/128) entries) */
 int ecb200_debug_tc_timeline(const float* hi, const float* lo, const float* xx, int B, int C, int N,
                              int k, int32_t* idx, void* workspace, long long* timeline, void* stream);
 

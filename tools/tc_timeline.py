@@ -14,14 +14,16 @@ hi = torch.empty(B * N, C, device=dev); lo = torch.empty_like(hi); xx = torch.em
 idx = torch.empty(B, N, k, device=dev, dtype=torch.int32)
 nb = L.load().ecb200_knn_tc_workspace_bytes(B, N, k)
 ws = torch.empty(nb, device=dev, dtype=torch.uint8)
-tl = torch.zeros(6 * 256, device=dev, dtype=torch.int64)
+ntile = B * ((N + 127) // 128)
+tl = torch.zeros(6 * 256 + 3 * ntile, device=dev, dtype=torch.int64)
 P = lambda t: c_void_p(t.data_ptr())
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
 L.call("ecb200_split_tf32", P(x), B, C, N, P(hi), P(lo), P(xx), st)
 for _ in range(3):
     L.call("ecb200_debug_tc_timeline", P(hi), P(lo), P(xx), B, C, N, k, P(idx), P(ws), P(tl), st)
 torch.cuda.synchronize()
-t = tl.cpu().view(6, 256)
+allc = tl.cpu()[6 * 256:].view(ntile, 3)
+t = tl.cpu()[:6 * 256].view(6, 256)
 t0 = int(t[5, 0])
 nct = (N + 127) // 128; nkb = C // 32
 rel = lambda v: (int(v) - t0) if int(v) else None
@@ -35,3 +37,14 @@ for g in (0, 1):
         print("   use", u, [rel(v) for v in t[2 + g, 4 * u:4 * u + 4]])
     print("   pass ends / pre-copy / post-copy / ranked:", [rel(v) for v in t[4, 8 * g:8 * g + 5]])
     print("   tau stage: start / sorted / done:", [rel(v) for v in t[4, 8 * g + 5:8 * g + 8]])
+
+# every CTA: start / duration (us) relative to the first start, by SM
+st0 = int(allc[:, 0].min())
+dur = (allc[:, 1] - allc[:, 0]).double() / 1e3
+beg = (allc[:, 0] - st0).double() / 1e3
+print(f"all CTAs: {ntile} on {len(set(allc[:, 2].tolist()))} SMs; kernel span {(int(allc[:, 1].max()) - st0) / 1e3:.1f} us; "
+      f"CTA duration us: min {dur.min():.1f} median {dur.median():.1f} max {dur.max():.1f}")
+first = beg < 1.0
+print(f"  first wave: {int(first.sum())} CTAs, duration median {dur[first].median():.1f} max {dur[first].max():.1f}; "
+      f"later CTAs: start median {beg[~first].median() if (~first).any() else 0:.1f} duration median "
+      f"{dur[~first].median() if (~first).any() else 0:.1f} max {dur[~first].max() if (~first).any() else 0:.1f}")
