@@ -32,8 +32,8 @@ SIGNATURES = {
     "ecb200_edge_gather": (P, P, P, I, I, I, I, P, P, P, P, P),
     "ecb200_bn_finalize": (P, P, P, P, P, I, F, I, P, P, P, P, P),
     "ecb200_bn_update_running": (P, I, F, P, P, P, P),
-    "ecb200_edge_apply": (P, P, P, F, I, I, I, P, P),
-    "ecb200_bwd_prep": (P, P, P, P, P, P, F, I, I, I, P, P, P),
+    "ecb200_edge_apply": (P, P, P, F, I, I, I, P, P, LL, P),
+    "ecb200_bwd_prep": (P, P, LL, P, P, P, P, P, F, I, I, I, P, P, P),
     "ecb200_bwd_finalize": (P, P, P, P, P, I, I, P, P, P, P, P),
     "ecb200_reverse_graph": (P, I, I, I, P, P, P, P),
     "ecb200_bwd_dense": (P, P, P, P, P, P, I, I, I, I, P, P),

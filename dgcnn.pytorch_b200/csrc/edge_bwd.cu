@@ -17,7 +17,8 @@ namespace {
 constexpr int BT = 256;
 
 __global__ void __launch_bounds__(256)
-bwd_prep_kernel(const float* __restrict__ gout, const float* __restrict__ sel,
+bwd_prep_kernel(const float* __restrict__ gout, const float* __restrict__ gout_pm, long long ld_pm,
+                const float* __restrict__ sel,
                 const float* __restrict__ a, const float* __restrict__ b,
                 const float* __restrict__ mean, const float* __restrict__ invstd, float slope, int N,
                 int Co, float* __restrict__ g, double* __restrict__ bstats) {
@@ -28,7 +29,7 @@ bwd_prep_kernel(const float* __restrict__ gout, const float* __restrict__ sel,
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int oc = o0 + ty + 8 * r, n = n0 + tx;
-    tile[ty + 8 * r][tx] = (oc < Co && n < N) ? gout[((size_t)bb * Co + oc) * N + n] : 0.f;
+    tile[ty + 8 * r][tx] = (gout && oc < Co && n < N) ? gout[((size_t)bb * Co + oc) * N + n] : 0.f;
   }
   __syncthreads();
   const int o = o0 + tx;
@@ -42,7 +43,9 @@ bwd_prep_kernel(const float* __restrict__ gout, const float* __restrict__ sel,
         const size_t m = (size_t)bb * N + n;
         const float s = sel[m * Co + o];
         const float y = fmaf(ao, s, bo);
-        const float gg = tile[tx][p] * (y > 0.f ? 1.f : slope);
+        float gin = tile[tx][p];
+        if (gout_pm) gin += gout_pm[m * ld_pm + o];  // gradient of the point-major copy of the output
+        const float gg = gin * (y > 0.f ? 1.f : slope);
         g[m * Co + o] = gg;
         db += (double)gg;
         dg += (double)(gg * ((s - mu) * rs));
@@ -242,13 +245,15 @@ unsigned group_grid(long long M, int Co) {
 
 }  // namespace
 
-extern "C" int ecb200_bwd_prep(const float* gout, const float* sel, const float* a, const float* b,
-                               const float* mean, const float* invstd, float slope, int B, int N,
-                               int Co, float* g, double* bstats, void* stream) {
-  ECB_REQUIRE(gout && sel && a && b && mean && invstd && g && bstats, "ecb200_bwd_prep: null pointer");
+extern "C" int ecb200_bwd_prep(const float* gout, const float* gout_pm, long long ld_pm, const float* sel,
+                               const float* a, const float* b, const float* mean, const float* invstd,
+                               float slope, int B, int N, int Co, float* g, double* bstats, void* stream) {
+  ECB_REQUIRE((gout || gout_pm) && sel && a && b && mean && invstd && g && bstats,
+              "ecb200_bwd_prep: null pointer");
   ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1 && Co >= 1, "ecb200_bwd_prep: bad shape");
+  ECB_REQUIRE(!gout_pm || ld_pm >= Co, "ecb200_bwd_prep: ld_pm=%lld smaller than Co=%d", ld_pm, Co);
   dim3 grid(ecb200::ceil_div(N, 32), ecb200::ceil_div(Co, 32), B);
-  bwd_prep_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(gout, sel, a, b, mean, invstd, slope,
+  bwd_prep_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(gout, gout_pm, ld_pm, sel, a, b, mean, invstd, slope,
                                                                  N, Co, g, bstats);
   ECB_LAUNCH_CHECK("bwd_prep_kernel");
   return ECB200_OK;

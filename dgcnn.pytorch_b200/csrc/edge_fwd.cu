@@ -150,11 +150,13 @@ __global__ void bn_update_running_kernel(const double* __restrict__ stats, int C
   if (threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
 }
 
-// [M,Co] -> [B,Co,N] with the BatchNorm affine and LeakyReLU fused into the transpose
+// [M,Co] -> [B,Co,N] with the BatchNorm affine and LeakyReLU fused into the transpose; the same
+// values optionally also go out point-major (out_pm[m*ld_pm + o]) for consumers that want rows
+// of channels (the 512-channel concat in front of conv5, models/dgcnn.py:100)
 __global__ void __launch_bounds__(256)
 edge_apply_kernel(const float* __restrict__ sel, const float* __restrict__ a,
                   const float* __restrict__ b, float slope, int N, int Co,
-                  float* __restrict__ out) {
+                  float* __restrict__ out, float* __restrict__ out_pm, long long ld_pm) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int n0 = blockIdx.x * 32, o0 = blockIdx.y * 32, bb = blockIdx.z;
@@ -164,9 +166,14 @@ edge_apply_kernel(const float* __restrict__ sel, const float* __restrict__ a,
   for (int r = 0; r < 4; ++r) {
     const int p = ty + 8 * r, n = n0 + p;
     float y = 0.f;
-    if (n < N && o < Co) y = ecb200::leaky(fmaf(ao, sel[((size_t)bb * N + n) * Co + o], bo), slope);
+    if (n < N && o < Co) {
+      const size_t m = (size_t)bb * N + n;
+      y = ecb200::leaky(fmaf(ao, sel[m * Co + o], bo), slope);
+      if (out_pm) out_pm[m * ld_pm + o] = y;
+    }
     tile[p][tx] = y;
   }
+  if (!out) return;
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -307,11 +314,14 @@ extern "C" int ecb200_bn_update_running(const double* stats, int Co, float momen
 }
 
 extern "C" int ecb200_edge_apply(const float* sel, const float* a, const float* b, float slope,
-                                 int B, int N, int Co, float* out, void* stream) {
-  ECB_REQUIRE(sel && a && b && out, "ecb200_edge_apply: null pointer");
+                                 int B, int N, int Co, float* out, float* out_pm, long long ld_pm,
+                                 void* stream) {
+  ECB_REQUIRE(sel && a && b && (out || out_pm), "ecb200_edge_apply: null pointer");
   ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1 && Co >= 1, "ecb200_edge_apply: bad shape");
+  ECB_REQUIRE(!out_pm || ld_pm >= Co, "ecb200_edge_apply: ld_pm=%lld smaller than Co=%d", ld_pm, Co);
   dim3 grid(ecb200::ceil_div(N, 32), ecb200::ceil_div(Co, 32), B);
-  edge_apply_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(sel, a, b, slope, N, Co, out);
+  edge_apply_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(sel, a, b, slope, N, Co, out, out_pm,
+                                                                    ld_pm);
   ECB_LAUNCH_CHECK("edge_apply_kernel");
   return ECB200_OK;
 }

@@ -67,13 +67,15 @@ def _edge_block(cin: int, cout: int) -> nn.Sequential:
 
 
 def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
-                   idx: Optional[torch.Tensor] = None, subtract_center: bool = False):
+                   idx: Optional[torch.Tensor] = None, subtract_center: bool = False,
+                   return_point_major: bool = False):
     """One EdgeConv layer = ``block(get_graph_feature(x, k)).max(-1)[0]`` of the
     reference (models/dgcnn.py:84-86), fused.  ``block`` is the reference's own
     ``nn.Sequential(Conv2d(2C,Co,1,bias=False), BatchNorm2d | SyncBatchNorm,
     LeakyReLU)``; its parameters and buffers are read at call time, so
     ``SyncBatchNorm.convert_sync_batchnorm`` and DDP keep working.
-    Returns (out [B,Co,N], idx int32 [B,N,k])."""
+    Returns (out [B,Co,N], idx int32 [B,N,k]); with ``return_point_major`` out is the pair
+    (out [B,Co,N], out_pm [B*N,Co]) of the same values in both layouts."""
     conv, bn, act = block[0], block[1], block[2]
     if conv.bias is not None or tuple(conv.kernel_size) != (1, 1):
         raise RuntimeError("edgeconv_block expects a bias-free 1x1 Conv2d")
@@ -97,7 +99,7 @@ def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
     slope = float(getattr(act, "negative_slope", 0.0))
     out = ops.edgeconv(x, idx, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                        bn.num_batches_tracked, bn.training, bn.momentum, bn.eps, slope,
-                       subtract_center, group, xhi, xlo)
+                       subtract_center, group, xhi, xlo, return_point_major)
     return out, idx
 
 
@@ -122,6 +124,10 @@ class DGCNN(nn.Module):
         self.conv5 = _edge_block(512, self.emb_dims)
         self.record_idx = False
         self.last_idx: List[torch.Tensor] = []
+        # the reference returns a contiguous [B, emb, N] tensor; internally the embedding is
+        # produced point-major (channels-last).  Consumers that only reduce over the points
+        # (DGCNN_cls) may set this to skip the final transposing copy.
+        self.strided_output = False
 
     def forward(self, x: torch.Tensor, idx_list=None) -> torch.Tensor:
         batch_size, _, num_points = x.size()
@@ -131,10 +137,15 @@ class DGCNN(nn.Module):
         h = x
         for layer, block in enumerate((self.conv1, self.conv2, self.conv3, self.conv4)):
             forced = None if idx_list is None else idx_list[layer].to(torch.int32)
-            h, idx = edgeconv_block(h, block, self.k, idx=forced,
-                                    subtract_center=self.subtract_center)
+            (h, h_pm), idx = edgeconv_block(h, block, self.k, idx=forced,
+                                            subtract_center=self.subtract_center,
+                                            return_point_major=True)
             if self.record_idx:
                 self.last_idx.append(idx)
-            feats.append(h)
-        h = torch.cat(feats, dim=1).unsqueeze(-1)        # [B,512,N,1]  dgcnn.py:100
-        return self.conv5(h).view(batch_size, -1, num_points)   # dgcnn.py:102
+            feats.append(h_pm)
+        # dgcnn.py:100: cat(x1..x4, dim=1) -> [B,512,N,1].  The fused layers also emit their output
+        # as rows of channels, so the concat is built channels-last ([B*N, 512] in memory): conv5
+        # (cuDNN) and its BatchNorm then run without NCHW<->NHWC transposes of 64-128 MiB tensors.
+        h = torch.cat(feats, dim=1).view(batch_size, num_points, 1, -1).permute(0, 3, 1, 2)   # NHWC strides
+        out = self.conv5(h).view(batch_size, -1, num_points)   # dgcnn.py:102
+        return out if self.strided_output else out.contiguous()

@@ -47,6 +47,7 @@ class DGCNN_cls(nn.Module):
     def __init__(self, args, output_channels: int = 40):
         super().__init__()
         self.backbone = DGCNN(args)
+        self.backbone.strided_output = True      # the head only reduces over the points
         self.head = ClsHead(self.backbone.emb_dims, output_channels,
                             float(getattr(args, "dropout", 0.5)))
 

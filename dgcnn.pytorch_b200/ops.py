@@ -230,9 +230,10 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
                     running_mean: Optional[Tensor], running_var: Optional[Tensor],
                     use_batch_stats: bool, eps: float, slope: float, subtract_center: bool,
                     group: int, save_for_bwd: bool, xhi: Optional[Tensor],
-                    xlo: Optional[Tensor]) -> List[Tensor]:
-    """Returns [out, sel, arg, esum, Y, Wcat, affine, stats]; ``affine`` is [4,Co] =
-    (mean, invstd, a, b).  Everything after ``out`` exists for the backward pass."""
+                    xlo: Optional[Tensor], emit_pm: bool) -> List[Tensor]:
+    """Returns [out, out_pm, sel, arg, esum, Y, Wcat, affine, stats]; ``out_pm`` [B*N, Co] is the
+    same output point-major (rows of channels; empty unless ``emit_pm``); ``affine`` is [4,Co] =
+    (mean, invstd, a, b).  Everything after ``out_pm`` exists for the backward pass."""
     _check_cuda_f32("x", x, 3)
     B, C, N = x.shape
     k = idx.shape[-1]
@@ -259,6 +260,7 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
         affine = torch.empty(4, Co, **f32)
         mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * Co * r) for r in range(4))
         out = torch.empty(B, Co, N, **f32)
+        out_pm = torch.empty(M, Co, **f32) if emit_pm else None
         _lib.call("ecb200_pack_weight", _ptr(w), Co, C, int(subtract_center), _ptr(Wcat), st)
         if xhi is not None and xlo is not None and point_gemm_uses_tensor_cores(C):
             # the per-point GEMM on the tensor cores, from the operands the kNN already made
@@ -277,26 +279,30 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
                   None if use_batch_stats else _ptr(running_mean),
                   None if use_batch_stats else _ptr(running_var),
                   int(use_batch_stats), float(eps), Co, mean, invstd, a, b, st)
-        _lib.call("ecb200_edge_apply", _ptr(sel), a, b, float(slope), B, N, Co, _ptr(out), st)
+        _lib.call("ecb200_edge_apply", _ptr(sel), a, b, float(slope), B, N, Co, _ptr(out), _ptr(out_pm),
+                  Co, st)
     if esum is None:
         esum = sel.new_empty(0)
-    return [out, sel, arg, esum, Y, Wcat, affine, stats]
+    if out_pm is None:
+        out_pm = sel.new_empty(0)
+    return [out, out_pm, sel, arg, esum, Y, Wcat, affine, stats]
 
 
 @edgeconv_fwd_op.register_fake
 def _(x, idx, weight, gamma, beta, running_mean, running_var, use_batch_stats, eps, slope,
-      subtract_center, group, save_for_bwd, xhi, xlo):
+      subtract_center, group, save_for_bwd, xhi, xlo, emit_pm):
     B, C, N = x.shape
     Co = weight.shape[0]
     M = B * N
     f = x.new_empty
-    return [f((B, Co, N)), f((M, Co)), f((M, Co), dtype=torch.uint8),
+    return [f((B, Co, N)), f((M, Co)) if emit_pm else f((0,)), f((M, Co)), f((M, Co), dtype=torch.uint8),
             f((M, Co)) if save_for_bwd else f((0,)), f((M, 2 * Co)), f((2 * Co, C)),
             f((4, Co)), f((2 * Co + 1,), dtype=torch.float64)]
 
 
 @torch.library.custom_op("edgeconv_b200::edgeconv_bwd", mutates_args=(), device_types="cuda")
-def edgeconv_bwd_op(gout: Tensor, x: Tensor, idx: Tensor, sel: Tensor, arg: Tensor, esum: Tensor,
+def edgeconv_bwd_op(gout: Optional[Tensor], gout_pm: Optional[Tensor], x: Tensor, idx: Tensor, sel: Tensor,
+                    arg: Tensor, esum: Tensor,
                     Y: Tensor, Wcat: Tensor, affine: Tensor, stats: Tensor, use_batch_stats: bool,
                     slope: float, subtract_center: bool, group: int, xhi: Optional[Tensor],
                     xlo: Optional[Tensor]) -> List[Tensor]:
@@ -306,14 +312,15 @@ def edgeconv_bwd_op(gout: Tensor, x: Tensor, idx: Tensor, sel: Tensor, arg: Tens
     Co = sel.shape[1]
     M = B * N
     dev = x.device
-    gout = gout.contiguous().float()
+    gout = None if gout is None else gout.contiguous().float()
+    gout_pm = None if gout_pm is None else gout_pm.contiguous().float()
     with torch.cuda.device(dev):
         st = _stream(x)
         f32 = dict(device=dev, dtype=torch.float32)
         g = torch.empty(M, Co, **f32)
         bstats = torch.zeros(2 * Co, device=dev, dtype=torch.float64)
         mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * Co * r) for r in range(4))
-        _lib.call("ecb200_bwd_prep", _ptr(gout), _ptr(sel), a, b, mean, invstd,
+        _lib.call("ecb200_bwd_prep", _ptr(gout), _ptr(gout_pm), Co, _ptr(sel), a, b, mean, invstd,
                   float(slope), B, N, Co, _ptr(g), _ptr(bstats), st)
         if use_batch_stats and group:
             bglobal = bstats.clone()
@@ -359,7 +366,7 @@ def edgeconv_bwd_op(gout: Tensor, x: Tensor, idx: Tensor, sel: Tensor, arg: Tens
 
 
 @edgeconv_bwd_op.register_fake
-def _(gout, x, idx, sel, arg, esum, Y, Wcat, affine, stats, use_batch_stats, slope,
+def _(gout, gout_pm, x, idx, sel, arg, esum, Y, Wcat, affine, stats, use_batch_stats, slope,
       subtract_center, group, xhi, xlo):
     B, C, N = x.shape
     Co = sel.shape[1]
@@ -369,8 +376,8 @@ def _(gout, x, idx, sel, arg, esum, Y, Wcat, affine, stats, use_batch_stats, slo
 
 def _ec_setup(ctx, inputs, output):
     (x, idx, weight, gamma, beta, _rm, _rv, use_batch_stats, _eps, slope, subtract_center, group,
-     save_for_bwd, _xhi, _xlo) = inputs
-    out, sel, arg, esum, Y, Wcat, affine, stats = output
+     save_for_bwd, _xhi, _xlo, _emit_pm) = inputs
+    out, out_pm, sel, arg, esum, Y, Wcat, affine, stats = output
     if not save_for_bwd:
         raise RuntimeError("edgeconv_b200: forward ran with save_for_bwd=False but a gradient "
                            "is required")
@@ -381,13 +388,13 @@ def _ec_setup(ctx, inputs, output):
 
 
 def _ec_backward(ctx, grads):
-    gout = grads[0]
-    n_in = 15
-    if gout is None:
+    gout, gout_pm = grads[0], grads[1]
+    n_in = 16
+    if gout is None and gout_pm is None:
         return (None,) * n_in
     x, idx, sel, arg, esum, Y, Wcat, affine, stats, xhi, xlo = ctx.saved_tensors
     use_batch_stats, slope, subtract_center, group = ctx.cfg
-    dx, dW, dgamma, dbeta = edgeconv_bwd_op(gout, x, idx, sel, arg, esum, Y, Wcat, affine, stats,
+    dx, dW, dgamma, dbeta = edgeconv_bwd_op(gout, gout_pm, x, idx, sel, arg, esum, Y, Wcat, affine, stats,
                                             use_batch_stats, slope, subtract_center, group, xhi, xlo)
     return (dx, None, dW.view(ctx.wshape), dgamma, dbeta) + (None,) * (n_in - 5)
 
@@ -422,7 +429,8 @@ def edgeconv(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor
              running_mean: Optional[Tensor], running_var: Optional[Tensor],
              num_batches_tracked: Optional[Tensor], training: bool, momentum: Optional[float] = 0.1,
              eps: float = 1e-5, slope: float = 0.2, subtract_center: bool = False,
-             group: int = 0, xhi: Optional[Tensor] = None, xlo: Optional[Tensor] = None) -> Tensor:
+             group: int = 0, xhi: Optional[Tensor] = None, xlo: Optional[Tensor] = None,
+             return_point_major: bool = False):
     """Fused EdgeConv block on a given kNN graph:
     max_k LeakyReLU(BatchNorm2d(Conv2d_1x1([x_j (- x_i) ; x_i])))  ->  [B, Co, N]
     (models/dgcnn.py:84-86 with :54-58).  BatchNorm semantics follow nn.BatchNorm2d:
@@ -434,7 +442,9 @@ def edgeconv(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor
     mom = -1.0 if momentum is None else float(momentum)
     res = edgeconv_fwd_op(x, idx, weight, gamma, beta, running_mean, running_var, use_batch_stats,
                           float(eps), float(slope), bool(subtract_center), int(group), bool(need_grad),
-                          xhi, xlo)
+                          xhi, xlo, bool(return_point_major))
     if update_running:
         bn_update_running_op(res[-1].detach(), running_mean, running_var, num_batches_tracked, mom)
+    if return_point_major:
+        return res[0], res[1]          # [B,Co,N] and the same values as [B*N, Co]
     return res[0]

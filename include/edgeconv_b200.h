@@ -158,17 +158,21 @@ int ecb200_bn_finalize(const double* stats, const float* gamma, const float* bet
 int ecb200_bn_update_running(const double* stats, int Co, float momentum, float* running_mean,
                              float* running_var, int64_t* num_batches_tracked, void* stream);
 
-/* out[b,o,n] = leaky_relu(a[o]*sel[m,o] + b[o], slope)   ([M,Co] -> [B,Co,N]) */
+/* out[b,o,n] = leaky_relu(a[o]*sel[m,o] + b[o], slope)   ([M,Co] -> [B,Co,N]); the same values
+ * optionally also point-major, out_pm[m*ld_pm + o] (rows of channels: a column slice of the
+ * 512-channel concat in front of conv5, dgcnn.py:100).  Either of out / out_pm may be NULL. */
 int ecb200_edge_apply(const float* sel, const float* a, const float* b, float slope, int B,
-                      int N, int Co, float* out, void* stream);
+                      int N, int Co, float* out, float* out_pm, long long ld_pm, void* stream);
 
 /* ---- EdgeConv backward ------------------------------------------------------------ */
 
-/* g[m,o] = gout[b,o,n] * (a*sel+b > 0 ? 1 : slope);  bstats[0..Co-1] += sum g (d beta),
- * bstats[Co..2Co-1] += sum g*(sel-mean)*invstd (d gamma); fp64, caller zero-fills. */
-int ecb200_bwd_prep(const float* gout, const float* sel, const float* a, const float* b,
-                    const float* mean, const float* invstd, float slope, int B, int N, int Co,
-                    float* g, double* bstats, void* stream);
+/* g[m,o] = (gout[b,o,n] + gout_pm[m*ld_pm+o]) * (a*sel+b > 0 ? 1 : slope): the gradients of the
+ * channel-major output and of its point-major copy (either may be NULL);
+ * bstats[0..Co-1] += sum g (d beta), bstats[Co..2Co-1] += sum g*(sel-mean)*invstd (d gamma);
+ * fp64, caller zero-fills. */
+int ecb200_bwd_prep(const float* gout, const float* gout_pm, long long ld_pm, const float* sel,
+                    const float* a, const float* b, const float* mean, const float* invstd,
+                    float slope, int B, int N, int Co, float* g, double* bstats, void* stream);
 
 /* dgamma/dbeta (fp32) from the LOCAL sums; c1 = a*dbeta_g/count, c2 = a*dgamma_g*invstd/count
  * from the GLOBAL sums (equal to local on one GPU); count = *count_dev, the global edge count
