@@ -44,6 +44,10 @@ SIGNATURES = {
     "ecb200_transpose_split_tf32": (P, I, I, P, P, P),
     "ecb200_gemm_dx_tc": (P, P, P, P, I, I, I, I, P, P),
     "ecb200_gemm_dw_tc": (P, P, P, P, LL, I, I, P, P),
+    "ecb200_colstats": (P, LL, I, P, P),
+    "ecb200_embed_pool": (P, P, P, F, I, I, I, P, P, P),
+    "ecb200_embed_pool_bwd_stats": (P, P, P, P, P, P, P, F, I, I, I, P, P),
+    "ecb200_embed_pool_bwd_dz": (P, P, P, P, P, P, P, P, F, I, I, I, P, P),
 }
 
 # kernels each entry point enqueues (memsets are not counted)

@@ -60,6 +60,17 @@ def get_graph_feature(x: torch.Tensor, k: int = 20, knn_only: bool = False,
     return ops.graph_feature_op(x, idx32, mode)
 
 
+def _sync_group(bn: nn.Module) -> int:
+    """Handle of the process group whose ranks share this BatchNorm's statistics (SyncBatchNorm in
+    training mode, main_partseg_dist.py:189); 0 = statistics stay local."""
+    if isinstance(bn, nn.SyncBatchNorm) and bn.training and torch.distributed.is_available() \
+            and torch.distributed.is_initialized():
+        pg = bn.process_group if bn.process_group is not None else torch.distributed.group.WORLD
+        if torch.distributed.get_world_size(pg) > 1:
+            return ops.register_group(pg)
+    return 0
+
+
 def _edge_block(cin: int, cout: int) -> nn.Sequential:
     return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=1, bias=False),
                          nn.BatchNorm2d(cout),
@@ -90,12 +101,7 @@ def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
             idx = ops.knn_tc_op(xhi, xlo, xx, B, N, int(k))
     if idx is None:
         idx = ops.knn_op(x.detach().contiguous(), int(k), False)   # order over k is irrelevant here
-    group = 0
-    if isinstance(bn, nn.SyncBatchNorm) and bn.training and torch.distributed.is_available() \
-            and torch.distributed.is_initialized():
-        pg = bn.process_group if bn.process_group is not None else torch.distributed.group.WORLD
-        if torch.distributed.get_world_size(pg) > 1:
-            group = ops.register_group(pg)
+    group = _sync_group(bn)
     slope = float(getattr(act, "negative_slope", 0.0))
     out = ops.edgeconv(x, idx, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                        bn.num_batches_tracked, bn.training, bn.momentum, bn.eps, slope,
@@ -129,7 +135,9 @@ class DGCNN(nn.Module):
         # (DGCNN_cls) may set this to skip the final transposing copy.
         self.strided_output = False
 
-    def forward(self, x: torch.Tensor, idx_list=None) -> torch.Tensor:
+    def _edge_features(self, x: torch.Tensor, idx_list=None) -> torch.Tensor:
+        """The four EdgeConv layers (dgcnn.py:84-98) -> their concatenated outputs (dgcnn.py:100) as a
+        channels-last [B,512,N,1] tensor ([B*N, 512] in memory)."""
         batch_size, _, num_points = x.size()
         feats = []
         if self.record_idx:
@@ -146,6 +154,21 @@ class DGCNN(nn.Module):
         # dgcnn.py:100: cat(x1..x4, dim=1) -> [B,512,N,1].  The fused layers also emit their output
         # as rows of channels, so the concat is built channels-last ([B*N, 512] in memory): conv5
         # (cuDNN) and its BatchNorm then run without NCHW<->NHWC transposes of 64-128 MiB tensors.
-        h = torch.cat(feats, dim=1).view(batch_size, num_points, 1, -1).permute(0, 3, 1, 2)   # NHWC strides
-        out = self.conv5(h).view(batch_size, -1, num_points)   # dgcnn.py:102
+        return torch.cat(feats, dim=1).view(batch_size, num_points, 1, -1).permute(0, 3, 1, 2)   # NHWC strides
+
+    def forward(self, x: torch.Tensor, idx_list=None) -> torch.Tensor:
+        batch_size, _, num_points = x.size()
+        out = self.conv5(self._edge_features(x, idx_list)).view(batch_size, -1, num_points)   # dgcnn.py:102
         return out if self.strided_output else out.contiguous()
+
+    def forward_pooled(self, x: torch.Tensor, idx_list=None) -> torch.Tensor:
+        """cat(max over the points, mean over the points) of ``forward(x)`` -> [B, 2*emb]: what
+        upstream DGCNN_cls computes from the embedding.  conv5's convolution runs in cuDNN; its
+        BatchNorm + LeakyReLU are fused with the pooling, so the [B, emb, N] tensor never exists."""
+        batch_size, _, num_points = x.size()
+        conv, bn, act = self.conv5[0], self.conv5[1], self.conv5[2]
+        z = conv(self._edge_features(x, idx_list))                       # [B,emb,N,1], channels-last
+        z = z.permute(0, 2, 3, 1).reshape(batch_size * num_points, -1)    # [B*N, emb] (a view)
+        return ops.embed_pool(z, batch_size, num_points, bn.weight, bn.bias, bn.running_mean,
+                              bn.running_var, bn.num_batches_tracked, bn.training, bn.momentum, bn.eps,
+                              float(getattr(act, "negative_slope", 0.0)), _sync_group(bn))

@@ -31,10 +31,12 @@ class ClsHead(nn.Module):
         self.linear3 = nn.Linear(256, output_channels)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        b = x.size(0)
-        # == adaptive_max_pool1d / adaptive_avg_pool1d over the points (upstream head), as
-        # plain reductions (torch's adaptive max pool kernel is ~20x slower at N=1024)
-        x = torch.cat((x.max(dim=-1)[0].view(b, -1), x.mean(dim=-1).view(b, -1)), 1)
+        if x.dim() == 3:
+            b = x.size(0)
+            # == adaptive_max_pool1d / adaptive_avg_pool1d over the points (upstream head), as
+            # plain reductions (torch's adaptive max pool kernel is ~20x slower at N=1024)
+            x = torch.cat((x.max(dim=-1)[0].view(b, -1), x.mean(dim=-1).view(b, -1)), 1)
+        # else: already pooled, [B, 2*emb] (DGCNN.forward_pooled)
         x = self.dp1(F.leaky_relu(self.bn6(self.linear1(x)), negative_slope=0.2))
         x = self.dp2(F.leaky_relu(self.bn7(self.linear2(x)), negative_slope=0.2))
         return self.linear3(x)
@@ -52,7 +54,7 @@ class DGCNN_cls(nn.Module):
                             float(getattr(args, "dropout", 0.5)))
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return self.head(self.backbone(x))
+        return self.head(self.backbone.forward_pooled(x))
 
 
 def cal_loss(pred: torch.Tensor, gold: torch.Tensor, smoothing: bool = True) -> torch.Tensor:

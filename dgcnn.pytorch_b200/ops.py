@@ -448,3 +448,121 @@ def edgeconv(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor
     if return_point_major:
         return res[0], res[1]          # [B,Co,N] and the same values as [B*N, Co]
     return res[0]
+
+
+# ------------------------------------------- conv5's BN + LeakyReLU + global max|avg pooling
+@torch.library.custom_op("edgeconv_b200::embed_pool_fwd", mutates_args=(), device_types="cuda")
+def embed_pool_fwd_op(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor,
+                      running_mean: Optional[Tensor], running_var: Optional[Tensor],
+                      use_batch_stats: bool, eps: float, slope: float, group: int) -> List[Tensor]:
+    """z [B*N, E] (conv5's raw output, point-major) -> [pooled [B,2E], arg [B,E] i32,
+    affine [4,E] = (mean, invstd, a, b), stats [2E+1] f64]:  pooled = (max_n | mean_n) of
+    LeakyReLU(BatchNorm(z)) -- dgcnn.py:75-78,:102 followed by upstream DGCNN_cls's pooling."""
+    _check_cuda_f32("z", z, 2)
+    M, E = z.shape
+    if M != B * N:
+        raise RuntimeError(f"edgeconv_b200: z has {M} rows, expected B*N = {B * N}")
+    if E % 4 != 0:
+        raise RuntimeError(f"edgeconv_b200: embedding width must be a multiple of 4, got {E}")
+    z = z.contiguous()
+    gamma_c, beta_c = gamma.detach().contiguous().float(), beta.detach().contiguous().float()
+    dev = z.device
+    with torch.cuda.device(dev):
+        st = _stream(z)
+        f32 = dict(device=dev, dtype=torch.float32)
+        stats = torch.zeros(2 * E + 1, device=dev, dtype=torch.float64)
+        affine = torch.empty(4, E, **f32)
+        mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * E * r) for r in range(4))
+        pooled = torch.empty(B, 2 * E, **f32)
+        arg = torch.empty(B, E, device=dev, dtype=torch.int32)
+        if use_batch_stats:
+            _lib.call("ecb200_colstats", _ptr(z), M, E, _ptr(stats), st)
+            if group:
+                dist.all_reduce(stats, group=_GROUPS[group])
+        _lib.call("ecb200_bn_finalize", _ptr(stats), _ptr(gamma_c), _ptr(beta_c),
+                  None if use_batch_stats else _ptr(running_mean),
+                  None if use_batch_stats else _ptr(running_var),
+                  int(use_batch_stats), float(eps), E, mean, invstd, a, b, st)
+        _lib.call("ecb200_embed_pool", _ptr(z), a, b, float(slope), B, N, E, _ptr(pooled), _ptr(arg), st)
+    return [pooled, arg, affine, stats]
+
+
+@embed_pool_fwd_op.register_fake
+def _(z, B, N, gamma, beta, running_mean, running_var, use_batch_stats, eps, slope, group):
+    E = z.shape[1]
+    f = z.new_empty
+    return [f((B, 2 * E)), f((B, E), dtype=torch.int32), f((4, E)), f((2 * E + 1,), dtype=torch.float64)]
+
+
+@torch.library.custom_op("edgeconv_b200::embed_pool_bwd", mutates_args=(), device_types="cuda")
+def embed_pool_bwd_op(gpool: Tensor, z: Tensor, arg: Tensor, affine: Tensor, stats: Tensor, B: int,
+                      N: int, use_batch_stats: bool, slope: float, group: int) -> List[Tensor]:
+    """-> [dz [B*N,E], dgamma [E], dbeta [E]]"""
+    M, E = z.shape
+    dev = z.device
+    gpool = gpool.contiguous().float()
+    with torch.cuda.device(dev):
+        st = _stream(z)
+        f32 = dict(device=dev, dtype=torch.float32)
+        mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * E * r) for r in range(4))
+        bstats = torch.zeros(2 * E, device=dev, dtype=torch.float64)
+        _lib.call("ecb200_embed_pool_bwd_stats", _ptr(z), _ptr(gpool), _ptr(arg), a, b, mean, invstd,
+                  float(slope), B, N, E, _ptr(bstats), st)
+        if use_batch_stats and group:
+            bglobal = bstats.clone()
+            dist.all_reduce(bglobal, group=_GROUPS[group])
+        else:
+            bglobal = bstats
+        dgamma = torch.empty(E, **f32)
+        dbeta = torch.empty(E, **f32)
+        cc = torch.empty(2, E, **f32)
+        c1, c2 = c_void_p(cc.data_ptr()), c_void_p(cc.data_ptr() + 4 * E)
+        _lib.call("ecb200_bwd_finalize", _ptr(bstats), _ptr(bglobal), c_void_p(stats.data_ptr() + 8 * 2 * E),
+                  a, invstd, int(use_batch_stats), E, _ptr(dgamma), _ptr(dbeta), c1, c2, st)
+        dz = torch.empty(M, E, **f32)
+        _lib.call("ecb200_embed_pool_bwd_dz", _ptr(z), _ptr(gpool), _ptr(arg), a, b, mean, c1, c2,
+                  float(slope), B, N, E, _ptr(dz), st)
+    return [dz, dgamma, dbeta]
+
+
+@embed_pool_bwd_op.register_fake
+def _(gpool, z, arg, affine, stats, B, N, use_batch_stats, slope, group):
+    E = z.shape[1]
+    return [z.new_empty(z.shape), z.new_empty((E,)), z.new_empty((E,))]
+
+
+def _ep_setup(ctx, inputs, output):
+    z, B, N, _g, _b, _rm, _rv, use_batch_stats, _eps, slope, group = inputs
+    _pooled, arg, affine, stats = output
+    ctx.save_for_backward(z, arg, affine, stats)
+    ctx.cfg = (B, N, use_batch_stats, slope, group)
+    ctx.set_materialize_grads(False)
+
+
+def _ep_backward(ctx, grads):
+    gpool = grads[0]
+    if gpool is None:
+        return (None,) * 11
+    z, arg, affine, stats = ctx.saved_tensors
+    B, N, use_batch_stats, slope, group = ctx.cfg
+    dz, dgamma, dbeta = embed_pool_bwd_op(gpool, z, arg, affine, stats, B, N, use_batch_stats, slope, group)
+    return (dz, None, None, dgamma, dbeta) + (None,) * 6
+
+
+embed_pool_fwd_op.register_autograd(_ep_backward, setup_context=_ep_setup)
+
+
+def embed_pool(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor, running_mean: Optional[Tensor],
+               running_var: Optional[Tensor], num_batches_tracked: Optional[Tensor], training: bool,
+               momentum: Optional[float] = 0.1, eps: float = 1e-5, slope: float = 0.2,
+               group: int = 0) -> Tensor:
+    """cat(max_n, mean_n) of LeakyReLU(BatchNorm(z)) over the N points of each cloud -> [B, 2E].
+    z [B*N, E] point-major; BatchNorm semantics as nn.BatchNorm2d / SyncBatchNorm (see edgeconv)."""
+    use_batch_stats = bool(training or running_mean is None or running_var is None)
+    update_running = bool(training and running_mean is not None)
+    mom = -1.0 if momentum is None else float(momentum)
+    res = embed_pool_fwd_op(z, int(B), int(N), gamma, beta, running_mean, running_var, use_batch_stats,
+                            float(eps), float(slope), int(group))
+    if update_running:
+        bn_update_running_op(res[3].detach(), running_mean, running_var, num_batches_tracked, mom)
+    return res[0]

@@ -222,6 +222,29 @@ int ecb200_gemm_dw_tc(const float* dYhi, const float* dYlo, const float* xhi, co
 int ecb200_unpack_weight_grad(const float* dWcat, int Co, int C, int subtract_center, float* dW,
                               void* stream);
 
+/* ---- "next" row f-2: conv5's BatchNorm2d + LeakyReLU (dgcnn.py:75-78, :102) fused with the global
+ * max | average pooling over the points of the classification head ---------------------------
+ * z [M, E] = conv5's raw output, point-major (cuDNN's output for a channels-last input); the
+ * activated [B, E, N] tensor is never written. */
+
+/* stats[0..E) += sum_m z, stats[E..2E) += sum_m z^2, stats[2E] += M  (fp64, caller zero-fills;
+ * the same [sum | sum of squares | count] layout ecb200_bn_finalize / _update_running consume) */
+int ecb200_colstats(const float* z, long long M, int E, double* stats, void* stream);
+/* pooled[b, o] = max_n LeakyReLU(a[o] z + b[o]),  pooled[b, E+o] = mean_n LeakyReLU(a[o] z + b[o]),
+ * arg[b, o] = the n that attains the max (smallest n among equals).  pooled [B, 2E], arg [B, E]. */
+int ecb200_embed_pool(const float* z, const float* a, const float* b, float slope, int B, int N,
+                      int E, float* pooled, int32_t* arg, void* stream);
+/* backward, pass 1: with dact[m,o] = (gpool[b,E+o]/N + [n == arg[b,o]] gpool[b,o]) * LeakyReLU'(a z + b):
+ * bstats[0..E) += sum dact (d beta), bstats[E..2E) += sum dact*(z-mean)*invstd (d gamma); fp64. */
+int ecb200_embed_pool_bwd_stats(const float* z, const float* gpool, const int32_t* arg,
+                                const float* a, const float* b, const float* mean,
+                                const float* invstd, float slope, int B, int N, int E,
+                                double* bstats, void* stream);
+/* backward, pass 2: dz[m,o] = a*dact - c1 - c2*(z - mean)  (c1, c2 from ecb200_bwd_finalize) */
+int ecb200_embed_pool_bwd_dz(const float* z, const float* gpool, const int32_t* arg, const float* a,
+                             const float* b, const float* mean, const float* c1, const float* c2,
+                             float slope, int B, int N, int E, float* dz, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

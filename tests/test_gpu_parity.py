@@ -406,3 +406,79 @@ def test_full_size_properties(ec):
     z = torch.nn.functional.batch_norm(z, None, None, gamma, beta, True, 0.1, 1e-5)
     yr = torch.nn.functional.leaky_relu(z, 0.2).max(-1)[0]
     assert_rel(y, yr, what="fused vs materialised")
+
+
+# ------------------------------------ conv5's BatchNorm + LeakyReLU fused with the cls pooling
+def _embed_pool_reference(z, B, N, gamma, beta, rm, rv, training, slope=0.2, eps=1e-5, momentum=0.1):
+    """dgcnn.py:75-78,:102 (BatchNorm2d + LeakyReLU of conv5's output) followed by upstream
+    DGCNN_cls's max | mean over the points, in plain torch on the dtype / device of z."""
+    E = z.shape[1]
+    zz = z.view(B, N, E).permute(0, 2, 1).unsqueeze(-1)                # [B,E,N,1]
+    y = torch.nn.functional.batch_norm(zz, rm, rv, gamma, beta, training, momentum, eps)
+    y = torch.nn.functional.leaky_relu(y, slope).squeeze(-1)           # [B,E,N]
+    return torch.cat((y.max(dim=-1)[0], y.mean(dim=-1)), dim=1)
+
+
+@pytest.mark.parametrize("B,N,E", [(4, 256, 64), (3, 77, 20), (2, 1024, 1024)])
+@pytest.mark.parametrize("training", [True, False])
+def test_embed_pool_vs_torch_fp64(ec, B, N, E, training):
+    gen = torch.Generator().manual_seed(B * 100 + N + E)
+    z = torch.randn(B * N, E, generator=gen) * 1.5 + 0.3
+    gamma = torch.randn(E, generator=gen) * 0.5 + 1.0
+    gamma[::3] *= -1.0                                                  # min path of the monotone max
+    beta = torch.randn(E, generator=gen) * 0.3
+    rm, rv = torch.randn(E, generator=gen) * 0.2, torch.rand(E, generator=gen) + 0.5
+    gout = torch.randn(B, 2 * E, generator=gen)
+    # fp64 reference
+    zr, gr, br = (t.double().clone().requires_grad_(True) for t in (z, gamma, beta))
+    rmr, rvr = rm.double().clone(), rv.double().clone()
+    pr = _embed_pool_reference(zr, B, N, gr, br, rmr, rvr, training)
+    (pr * gout.double()).sum().backward()
+    d = dev()
+    zg, gg, bg = (t.to(d).requires_grad_(True) for t in (z, gamma, beta))
+    rmg, rvg = rm.to(d), rv.to(d)
+    nbt = torch.zeros((), dtype=torch.int64, device=d)
+    pg = ec.ops.embed_pool(zg, B, N, gg, bg, rmg, rvg, nbt, training)
+    (pg * gout.to(d)).sum().backward()
+    assert_rel(pg, pr, what="pooled")
+    assert_rel(zg.grad, zr.grad, what="dz")
+    assert_rel(gg.grad, gr.grad, what="dgamma")
+    assert_rel(bg.grad, br.grad, what="dbeta")
+    assert_rel(rmg, rmr, rel=1e-5, what="running_mean")
+    assert_rel(rvg, rvr, rel=1e-5, what="running_var")
+    assert int(nbt) == (1 if training else 0)
+
+
+def test_dgcnn_cls_pooled_path_equals_unfused(ec):
+    """DGCNN_cls (conv5's BN + LeakyReLU fused with the pooling) against the same weights run as
+    backbone.forward() -> [B,emb,N] -> torch max | mean -> head, on the device, same graphs."""
+    torch.manual_seed(11)
+    args = SimpleNamespace(emb_dims=256, k=12, dropout=0.0)
+    net = ec.DGCNN_cls(args).to(dev()).train()
+    x = orc.synthetic_xyz(3, 200, seed=4).to(dev())
+    y = torch.randint(0, 40, (3,), device=dev())
+
+    def run(fused):
+        net.zero_grad(set_to_none=True)
+        sd = {k: v.clone() for k, v in net.state_dict().items()}
+        logits = net(x) if fused else net.head(net.backbone(x))
+        loss = ec.cal_loss(logits, y)
+        loss.backward()
+        grads = {n: p.grad.clone() for n, p in net.named_parameters()}
+        after = {k: v.clone() for k, v in net.state_dict().items()}
+        net.load_state_dict(sd)                   # undo the running-statistics update
+        return logits.detach(), grads, after
+
+    la, ga, sa = run(True)
+    lb, gb, sb = run(False)
+    assert_rel(la, lb, what="logits")
+    for n in ga:
+        if gb[n].abs().max().item() < 1e-5:       # biases feeding a BatchNorm: gradient is 0 up to rounding
+            assert ga[n].abs().max().item() < 1e-5, n
+            continue
+        assert_rel(ga[n], gb[n], rel=2e-4, what=f"grad {n}")
+    for k in sa:
+        if sa[k].dtype.is_floating_point:
+            assert_rel(sa[k], sb[k], rel=1e-5, what=f"buffer {k}")
+        else:
+            assert torch.equal(sa[k], sb[k]), k
