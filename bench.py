@@ -425,7 +425,7 @@ def run_b200(a):
                    "l2": "256 MiB buffer rewritten between timed steps (L2 flush)",
                    "cuda_graph": use_graph,
                    "eager_ms_per_step": eager_ms, "graph_ms_per_step": graph_ms,
-                   "graph_error": graph_err, "conv5_and_head": "torch (cuDNN/cuBLAS, library defaults)",
+                   "graph_error": graph_err, "conv5_and_head": "conv5 GEMM in cuDNN (library default TF32) on the channels-last concat; its BatchNorm + LeakyReLU + max|avg pooling in own kernels (embed_pool); 3 head linears in torch",
                    "grad_sync": "one flat NCCL all-reduce per step" if world > 1 else None},
         "clocks": clocks,
         "e2e": {"value": clouds / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,

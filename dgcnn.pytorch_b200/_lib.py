@@ -36,8 +36,8 @@ SIGNATURES = {
     "ecb200_bwd_prep": (P, P, LL, P, P, P, P, P, F, I, I, I, P, P, P),
     "ecb200_bwd_finalize": (P, P, P, P, P, I, I, P, P, P, P, P),
     "ecb200_reverse_graph": (P, I, I, I, P, P, P, P),
-    "ecb200_bwd_dense": (P, P, P, P, P, P, I, I, I, I, P, P),
-    "ecb200_bwd_scatter": (P, P, P, P, P, P, P, P, I, I, I, I, P, P),
+    "ecb200_bwd_dense": (P, P, P, P, P, P, I, I, I, I, P, P, P, P, P),
+    "ecb200_bwd_scatter": (P, P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P),
     "ecb200_gemm_dx": (P, P, I, I, I, I, P, P),
     "ecb200_gemm_dw": (P, P, I, I, I, I, P, P),
     "ecb200_unpack_weight_grad": (P, I, I, I, P, P),

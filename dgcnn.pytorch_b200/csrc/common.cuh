@@ -67,6 +67,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ float leaky(float y, float slope) { return y > 0.f ? y : y * slope; }
 
+// round to tf32 (nearest, ties away): hi = tf32_rna(v), lo = tf32_rna(v - hi) is the operand pair of
+// the 3xTF32 tensor-core products
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // streaming (read-once) 128-bit load that does not pollute L1
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
   float4 r;

@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(BT)
 bwd_dense_kernel(const float* __restrict__ Y, const int32_t* __restrict__ rowptr,
                  const int32_t* __restrict__ src, const float* __restrict__ mean,
                  const float* __restrict__ c1, const float* __restrict__ c2, int training, int Co,
-                 long long M, float* __restrict__ dY) {
+                 long long M, float* __restrict__ dY, const float* __restrict__ dU_in,
+                 float* __restrict__ dYhi, float* __restrict__ dYlo) {
   constexpr int SPW = 32 / LPP;
   const int lane = threadIdx.x & 31, sl = lane % LPP;
   const int G = Co / (4 * LPP), Co2 = 2 * Co;
@@ -176,7 +177,21 @@ bwd_dense_kernel(const float* __restrict__ Y, const int32_t* __restrict__ rowptr
       out.z = -k1.z * deg - k2.z * (deg * (u.z - mu.z) + T.z);
       out.w = -k1.w * deg - k2.w * (deg * (u.w - mu.w) + T.w);
     }
-    *reinterpret_cast<float4*>(dY + m * Co2 + c) = out;
+    if (dU_in) {
+      // fused mode: the sparse part was scattered into dU_in [M,Co] before; the sum goes out as the
+      // tf32 hi/lo operand pair of the tensor-core GEMMs (no fp32 dY, no separate split pass)
+      const float4 sp = *reinterpret_cast<const float4*>(dU_in + m * Co + c);
+      out.x += sp.x; out.y += sp.y; out.z += sp.z; out.w += sp.w;
+      float4 h, l;
+      h.x = ecb200::tf32_rna(out.x); l.x = ecb200::tf32_rna(out.x - h.x);
+      h.y = ecb200::tf32_rna(out.y); l.y = ecb200::tf32_rna(out.y - h.y);
+      h.z = ecb200::tf32_rna(out.z); l.z = ecb200::tf32_rna(out.z - h.z);
+      h.w = ecb200::tf32_rna(out.w); l.w = ecb200::tf32_rna(out.w - h.w);
+      *reinterpret_cast<float4*>(dYhi + m * Co2 + c) = h;
+      *reinterpret_cast<float4*>(dYlo + m * Co2 + c) = l;
+    } else {
+      *reinterpret_cast<float4*>(dY + m * Co2 + c) = out;
+    }
   }
 }
 
@@ -187,7 +202,8 @@ bwd_scatter_kernel(const float* __restrict__ g, const float* __restrict__ esum,
                    const uint8_t* __restrict__ arg, const int32_t* __restrict__ idx,
                    const float* __restrict__ a, const float* __restrict__ mean,
                    const float* __restrict__ c1, const float* __restrict__ c2, int N, int k, int Co,
-                   long long M, float* __restrict__ dY) {
+                   long long M, float* __restrict__ dY, float* __restrict__ dU_acc,
+                   float* __restrict__ dYhi, float* __restrict__ dYlo) {
   constexpr int SPW = 32 / LPP;
   const int lane = threadIdx.x & 31, sl = lane % LPP;
   const int G = Co / (4 * LPP), Co2 = 2 * Co;
@@ -213,12 +229,28 @@ bwd_scatter_kernel(const float* __restrict__ g, const float* __restrict__ esum,
     dv.y = ag.y - kf * k1.y - k2.y * (es.y - kf * mu.y);
     dv.z = ag.z - kf * k1.z - k2.z * (es.z - kf * mu.z);
     dv.w = ag.w - kf * k1.w - k2.w * (es.w - kf * mu.w);
-    *reinterpret_cast<float4*>(dY + m * Co2 + Co + c) = dv;
     const int32_t* irow = idx + m * k;
-    atomicAdd(dY + (base + irow[aj.x]) * Co2 + c + 0, ag.x);
-    atomicAdd(dY + (base + irow[aj.y]) * Co2 + c + 1, ag.y);
-    atomicAdd(dY + (base + irow[aj.z]) * Co2 + c + 2, ag.z);
-    atomicAdd(dY + (base + irow[aj.w]) * Co2 + c + 3, ag.w);
+    if (dU_acc) {
+      // fused mode: dV is final here and goes out as tf32 hi/lo; the sparse part of dU accumulates
+      // in dU_acc [M,Co] (zero-filled by the caller), finished by bwd_dense_kernel
+      float4 h, l;
+      h.x = ecb200::tf32_rna(dv.x); l.x = ecb200::tf32_rna(dv.x - h.x);
+      h.y = ecb200::tf32_rna(dv.y); l.y = ecb200::tf32_rna(dv.y - h.y);
+      h.z = ecb200::tf32_rna(dv.z); l.z = ecb200::tf32_rna(dv.z - h.z);
+      h.w = ecb200::tf32_rna(dv.w); l.w = ecb200::tf32_rna(dv.w - h.w);
+      *reinterpret_cast<float4*>(dYhi + m * Co2 + Co + c) = h;
+      *reinterpret_cast<float4*>(dYlo + m * Co2 + Co + c) = l;
+      atomicAdd(dU_acc + (base + irow[aj.x]) * Co + c + 0, ag.x);
+      atomicAdd(dU_acc + (base + irow[aj.y]) * Co + c + 1, ag.y);
+      atomicAdd(dU_acc + (base + irow[aj.z]) * Co + c + 2, ag.z);
+      atomicAdd(dU_acc + (base + irow[aj.w]) * Co + c + 3, ag.w);
+    } else {
+      *reinterpret_cast<float4*>(dY + m * Co2 + Co + c) = dv;
+      atomicAdd(dY + (base + irow[aj.x]) * Co2 + c + 0, ag.x);
+      atomicAdd(dY + (base + irow[aj.y]) * Co2 + c + 1, ag.y);
+      atomicAdd(dY + (base + irow[aj.z]) * Co2 + c + 2, ag.z);
+      atomicAdd(dY + (base + irow[aj.w]) * Co2 + c + 3, ag.w);
+    }
   }
 }
 
@@ -292,15 +324,18 @@ extern "C" int ecb200_reverse_graph(const int32_t* idx, int B, int N, int k, int
 
 extern "C" int ecb200_bwd_dense(const float* Y, const int32_t* rowptr, const int32_t* src,
                                 const float* mean, const float* c1, const float* c2, int training,
-                                int B, int N, int Co, float* dY, void* stream) {
-  ECB_REQUIRE(Y && mean && c1 && c2 && dY, "ecb200_bwd_dense: null pointer");
+                                int B, int N, int Co, float* dY, const float* dU_in, float* dYhi,
+                                float* dYlo, void* stream) {
+  ECB_REQUIRE(Y && mean && c1 && c2, "ecb200_bwd_dense: null pointer");
+  ECB_REQUIRE(dU_in ? (dYhi && dYlo) : dY != nullptr,
+              "ecb200_bwd_dense: needs dY (plain mode) or dU_in + dYhi + dYlo (fused mode)");
   ECB_REQUIRE(!training || (rowptr && src), "ecb200_bwd_dense: training needs the reverse graph");
   ECB_REQUIRE(B >= 1 && N >= 1 && Co >= 4 && Co % 4 == 0, "ecb200_bwd_dense: bad shape");
   const long long M = (long long)B * N;
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(L)                                                                                  \
   bwd_dense_kernel<L><<<group_grid<L>(M, Co), BT, 0, st>>>(Y, rowptr, src, mean, c1, c2, training, \
-                                                         Co, M, dY)
+                                                         Co, M, dY, dU_in, dYhi, dYlo)
   ECB_DISPATCH_LPP(Co, CALL);
 #undef CALL
   ECB_LAUNCH_CHECK("bwd_dense_kernel");
@@ -310,14 +345,16 @@ extern "C" int ecb200_bwd_dense(const float* Y, const int32_t* rowptr, const int
 extern "C" int ecb200_bwd_scatter(const float* g, const float* esum, const uint8_t* arg,
                                   const int32_t* idx, const float* a, const float* mean,
                                   const float* c1, const float* c2, int B, int N, int k, int Co,
-                                  float* dY, void* stream) {
-  ECB_REQUIRE(g && esum && arg && idx && a && mean && c1 && c2 && dY, "ecb200_bwd_scatter: null pointer");
+                                  float* dY, float* dU_acc, float* dYhi, float* dYlo, void* stream) {
+  ECB_REQUIRE(g && esum && arg && idx && a && mean && c1 && c2, "ecb200_bwd_scatter: null pointer");
+  ECB_REQUIRE(dU_acc ? (dYhi && dYlo) : dY != nullptr,
+              "ecb200_bwd_scatter: needs dY (plain mode) or dU_acc + dYhi + dYlo (fused mode)");
   ECB_REQUIRE(B >= 1 && N >= 1 && k >= 1 && Co >= 4 && Co % 4 == 0, "ecb200_bwd_scatter: bad shape");
   const long long M = (long long)B * N;
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(L)                                                                                   \
   bwd_scatter_kernel<L><<<group_grid<L>(M, Co), BT, 0, st>>>(g, esum, arg, idx, a, mean, c1, c2, N, \
-                                                           k, Co, M, dY)
+                                                           k, Co, M, dY, dU_acc, dYhi, dYlo)
   ECB_DISPATCH_LPP(Co, CALL);
 #undef CALL
   ECB_LAUNCH_CHECK("bwd_scatter_kernel");

@@ -334,31 +334,37 @@ def edgeconv_bwd_op(gout: Optional[Tensor], gout_pm: Optional[Tensor], x: Tensor
         _lib.call("ecb200_bwd_finalize", _ptr(bstats), _ptr(bglobal),
                   c_void_p(stats.data_ptr() + 8 * 2 * Co), a, invstd,
                   int(use_batch_stats), Co, _ptr(dgamma), _ptr(dbeta), c1, c2, st)
-        dY = torch.empty(M, 2 * Co, **f32)
         rowptr = src = None
         if use_batch_stats:
             rowptr = torch.empty(M + 1, device=dev, dtype=torch.int32)
             src = torch.empty(M * k, device=dev, dtype=torch.int32)
             cursor = torch.empty(M, device=dev, dtype=torch.int32)
             _lib.call("ecb200_reverse_graph", _ptr(idx), B, N, k, _ptr(rowptr), _ptr(src), _ptr(cursor), st)
-        _lib.call("ecb200_bwd_dense", _ptr(Y), _ptr(rowptr), _ptr(src), mean, c1, c2,
-                  int(use_batch_stats), B, N, Co, _ptr(dY), st)
-        _lib.call("ecb200_bwd_scatter", _ptr(g), _ptr(esum), _ptr(arg), _ptr(idx), a, mean,
-                  c1, c2, B, N, k, Co, _ptr(dY), st)
         dx = torch.empty(B, C, N, **f32)
         dWcat = torch.empty(2 * Co, C, **f32)
         dW = torch.empty(Co, 2 * C, **f32)
         if xhi is not None and xlo is not None and bwd_gemm_uses_tensor_cores(C, Co):
-            # both backward GEMMs on the tensor cores (3xTF32) from tf32 hi/lo halves
+            # tensor-core GEMMs (3xTF32): the two graph kernels write dY = [dU | dV] directly as
+            # tf32 hi/lo halves -- sparse scatter first (into a zeroed [M,Co] accumulator), then
+            # the dense BatchNorm terms are added and the sum is split
             dYs = torch.empty(2, M, 2 * Co, **f32)
+            dU = torch.zeros(M, Co, **f32)
             wT = torch.empty(2, C, 2 * Co, **f32)
-            _lib.call("ecb200_split_rows_tf32", _ptr(dY), M * 2 * Co, _ptr(dYs[0]), _ptr(dYs[1]), st)
+            _lib.call("ecb200_bwd_scatter", _ptr(g), _ptr(esum), _ptr(arg), _ptr(idx), a, mean, c1, c2,
+                      B, N, k, Co, None, _ptr(dU), _ptr(dYs[0]), _ptr(dYs[1]), st)
+            _lib.call("ecb200_bwd_dense", _ptr(Y), _ptr(rowptr), _ptr(src), mean, c1, c2,
+                      int(use_batch_stats), B, N, Co, None, _ptr(dU), _ptr(dYs[0]), _ptr(dYs[1]), st)
             _lib.call("ecb200_transpose_split_tf32", _ptr(Wcat), 2 * Co, C, _ptr(wT[0]), _ptr(wT[1]), st)
             _lib.call("ecb200_gemm_dx_tc", _ptr(dYs[0]), _ptr(dYs[1]), _ptr(wT[0]), _ptr(wT[1]), B, C, N,
                       2 * Co, _ptr(dx), st)
             _lib.call("ecb200_gemm_dw_tc", _ptr(dYs[0]), _ptr(dYs[1]), _ptr(xhi), _ptr(xlo), M, C, 2 * Co,
                       _ptr(dWcat), st)
         else:
+            dY = torch.empty(M, 2 * Co, **f32)
+            _lib.call("ecb200_bwd_dense", _ptr(Y), _ptr(rowptr), _ptr(src), mean, c1, c2,
+                      int(use_batch_stats), B, N, Co, _ptr(dY), None, None, None, st)
+            _lib.call("ecb200_bwd_scatter", _ptr(g), _ptr(esum), _ptr(arg), _ptr(idx), a, mean,
+                      c1, c2, B, N, k, Co, _ptr(dY), None, None, None, st)
             _lib.call("ecb200_gemm_dx", _ptr(dY), _ptr(Wcat), B, C, N, 2 * Co, _ptr(dx), st)
             _lib.call("ecb200_gemm_dw", _ptr(dY), _ptr(x), B, C, N, 2 * Co, _ptr(dWcat), st)
         _lib.call("ecb200_unpack_weight_grad", _ptr(dWcat), Co, C, int(subtract_center), _ptr(dW), st)

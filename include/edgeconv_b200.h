@@ -188,16 +188,23 @@ int ecb200_bwd_finalize(const double* bstats_local, const double* bstats_global,
 int ecb200_reverse_graph(const int32_t* idx, int B, int N, int k, int32_t* rowptr,
                          int32_t* src, int32_t* cursor, void* stream);
 
-/* dY[:, :Co] (= dU) <- the dense BatchNorm-backward terms through the reverse graph
- * (training), or zeros (eval). */
+/* dU = the dense BatchNorm-backward terms through the reverse graph (training; zeros in eval).
+ * Plain mode (dU_in == NULL): written to dY[:, :Co] (fp32 [M,2Co]); run BEFORE ecb200_bwd_scatter,
+ * which adds the sparse part.  Fused mode: dU_in [M,Co] already holds the sparse part
+ * (ecb200_bwd_scatter ran first); the sum is written as tf32 hi/lo halves into
+ * dYhi/dYlo[:, :Co] -- the operands of ecb200_gemm_dx_tc / _dw_tc, no fp32 dY, no split pass. */
 int ecb200_bwd_dense(const float* Y, const int32_t* rowptr, const int32_t* src,
                      const float* mean, const float* c1, const float* c2, int training, int B,
-                     int N, int Co, float* dY, void* stream);
+                     int N, int Co, float* dY, const float* dU_in, float* dYhi, float* dYlo,
+                     void* stream);
 
-/* dY[:, Co:] (= dV) and the sparse scatter of a*g into dU rows through the arg slots. */
+/* dV and the sparse scatter of a*g into dU rows through the arg slots.
+ * Plain mode (dU_acc == NULL): dV -> dY[:, Co:], atomics -> dY[:, :Co].
+ * Fused mode: dV -> tf32 hi/lo in dYhi/dYlo[:, Co:], atomics -> dU_acc [M,Co] (caller zero-fills). */
 int ecb200_bwd_scatter(const float* g, const float* esum, const uint8_t* arg,
                        const int32_t* idx, const float* a, const float* mean, const float* c1,
-                       const float* c2, int B, int N, int k, int Co, float* dY, void* stream);
+                       const float* c2, int B, int N, int k, int Co, float* dY, float* dU_acc,
+                       float* dYhi, float* dYlo, void* stream);
 
 /* dx[B,C,N] = dY . Wcat ;  dWcat[2Co,C] = dY^T . x^T (callee zero-fills) */
 int ecb200_gemm_dx(const float* dY, const float* Wcat, int B, int C, int N, int Co2, float* dx,
