@@ -257,6 +257,7 @@ def run_b200(a):
     args = SimpleNamespace(emb_dim=a.emb, k=k, dropout=0.5)
     model = ec.DGCNN_cls(args).to(dev).train()
     sync = None
+    stats_exchange = None
     if world > 1:
         # SyncBatchNorm semantics for every BN (the EdgeConv ones exchange their statistics
         # inside the fused op); gradients averaged by one flat all-reduce per step
@@ -265,6 +266,15 @@ def run_b200(a):
         for p in model.parameters():          # identical replicas
             dist.broadcast(p.data, 0)
         sync = FlatGradSync(model.parameters())
+        if os.environ.get("ECB200_STATS_EXCHANGE", "peer") == "peer":
+            try:   # BatchNorm statistics over NVLink peer memory, one kernel per exchange
+                from dgcnn_pytorch_b200.dist import PeerStatsExchange
+                peer_exchange = PeerStatsExchange.enable()
+                stats_exchange = "one-kernel push exchange over NVLink peer memory (symmetric memory)"
+            except Exception as exc:  # noqa: BLE001 - transport fallback, reported in the JSON line
+                stats_exchange = f"NCCL all-reduce (peer memory unavailable: {type(exc).__name__}: {exc})"[:160]
+        else:
+            stats_exchange = "NCCL all-reduce"
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
 
     import edgeconv_oracle as orc   # only for the synthetic-input generator and the cpu_baseline leg
@@ -426,7 +436,8 @@ def run_b200(a):
                    "cuda_graph": use_graph,
                    "eager_ms_per_step": eager_ms, "graph_ms_per_step": graph_ms,
                    "graph_error": graph_err, "conv5_and_head": "conv5 GEMM in cuDNN (library default TF32) on the channels-last concat; its BatchNorm + LeakyReLU + max|avg pooling in own kernels (embed_pool); 3 head linears in torch",
-                   "grad_sync": "one flat NCCL all-reduce per step" if world > 1 else None},
+                   "grad_sync": "one flat NCCL all-reduce per step" if world > 1 else None,
+                   "bn_stats_exchange": stats_exchange},
         "clocks": clocks,
         "e2e": {"value": clouds / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "error": e2e_err},

@@ -44,6 +44,7 @@ SIGNATURES = {
     "ecb200_transpose_split_tf32": (P, I, I, P, P, P),
     "ecb200_gemm_dx_tc": (P, P, P, P, I, I, I, I, P, P),
     "ecb200_gemm_dw_tc": (P, P, P, P, LL, I, I, P, P),
+    "ecb200_peer_allreduce": (P, I, P, I, I, P, P),
     "ecb200_colstats": (P, LL, I, P, P),
     "ecb200_embed_pool": (P, P, P, F, I, I, I, P, P, P),
     "ecb200_embed_pool_bwd_stats": (P, P, P, P, P, P, P, F, I, I, I, P, P),
@@ -55,7 +56,8 @@ KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
 KERNELS_PER_CALL["ecb200_reverse_graph"] = 3
 
 # entry points that do not return an error code
-PLAIN = {"ecb200_version": 0, "ecb200_last_error": 0, "ecb200_knn_tc_workspace_bytes": 3}
+PLAIN = {"ecb200_version": 0, "ecb200_last_error": 0, "ecb200_knn_tc_workspace_bytes": 3,
+         "ecb200_peer_buffer_bytes": 1}
 
 _lib = None
 launch_count = 0          # kernels of this library enqueued so far (bench.py's gpu_launches)
@@ -86,6 +88,8 @@ def load() -> ctypes.CDLL:
         fn.restype = c_int
     lib.ecb200_knn_tc_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.ecb200_knn_tc_workspace_bytes.restype = c_size_t
+    lib.ecb200_peer_buffer_bytes.argtypes = [c_int]
+    lib.ecb200_peer_buffer_bytes.restype = c_size_t
     lib.ecb200_version.argtypes = []
     lib.ecb200_version.restype = c_int
     lib.ecb200_last_error.argtypes = []

@@ -86,3 +86,59 @@ class FlatGradSync:
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / self.world)
+
+
+class PeerStatsExchange:
+    """The SyncBatchNorm statistics exchange as ONE kernel over NVLink peer memory.
+
+    The exchange is a few hundred fp64 values per BatchNorm layer, ten times per step: pure
+    latency.  Instead of an NCCL collective every rank pushes its vector straight into a slot
+    of every peer's buffer (plain stores over NVLink into memory mapped with
+    torch.distributed._symmetric_memory), raises a flag, waits for the peers' flags and sums
+    the vectors in rank order (csrc/peer_exchange.cu).  No host involvement, capturable in a
+    CUDA graph, bit-identical results on every rank.
+
+        ex = PeerStatsExchange.enable()        # after init_process_group, once per process
+    """
+
+    def __init__(self, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        self.group = dist.group.WORLD if group is None else group
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        lib = _lib.load()
+        nbytes = lib.ecb200_peer_buffer_bytes(self.world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.bufs_dev = int(self.handle.buffer_ptrs_dev)     # device array of `world` base pointers
+        self.seq = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.max_values = (nbytes - 2 * self.world * 8) // (2 * self.world * 8)
+        torch.cuda.synchronize()
+        dist.barrier(self.group)                              # every buffer is zeroed before any push
+
+    @classmethod
+    def enable(cls, group=None) -> "PeerStatsExchange":
+        """Create the exchange for ``group`` (default: WORLD) and route the EdgeConv / embed_pool
+        BatchNorm statistics of that group through it."""
+        from . import ops
+        ex = cls(group)
+        ops.set_peer_exchange(ops.register_group(ex.group), ex)
+        return ex
+
+    def allreduce_(self, stats: torch.Tensor) -> torch.Tensor:
+        """In-place SUM of an fp64 device vector over the group (the op the kernels use)."""
+        from ctypes import c_void_p
+
+        from . import _lib
+        if stats.dtype != torch.float64 or not stats.is_cuda or not stats.is_contiguous():
+            raise TypeError("PeerStatsExchange.allreduce_ takes a contiguous fp64 CUDA tensor")
+        if stats.numel() > self.max_values:
+            raise ValueError(f"at most {self.max_values} values per exchange, got {stats.numel()}")
+        _lib.call("ecb200_peer_allreduce", c_void_p(stats.data_ptr()), stats.numel(), c_void_p(self.bufs_dev),
+                  self.rank, self.world, c_void_p(self.seq.data_ptr()),
+                  c_void_p(torch.cuda.current_stream().cuda_stream))
+        return stats

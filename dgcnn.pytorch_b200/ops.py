@@ -29,6 +29,7 @@ MAX_K = 64
 # torch.distributed process groups cannot travel through an op schema: ops take an
 # integer handle into this table (0 = no cross-rank BatchNorm statistics).
 _GROUPS = {}
+_PEER = {}      # group handle -> dist.PeerStatsExchange (statistics exchange over NVLink peer memory)
 
 
 def register_group(group) -> int:
@@ -42,6 +43,25 @@ def register_group(group) -> int:
     h = len(_GROUPS) + 1
     _GROUPS[h] = group
     return h
+
+
+def set_peer_exchange(handle: int, exchange) -> None:
+    """Route the BatchNorm-statistics all-reduce of group ``handle`` through a one-kernel exchange
+    over peer memory (dist.PeerStatsExchange) instead of NCCL; None switches back."""
+    if exchange is None:
+        _PEER.pop(handle, None)
+    else:
+        _PEER[handle] = exchange
+
+
+def _allreduce_stats(stats: Tensor, handle: int) -> None:
+    """In-place SUM of the fp64 statistics vector over the ranks of group ``handle``."""
+    peer = _PEER.get(handle)
+    if peer is not None and stats.numel() <= peer.max_values:
+        _lib.call("ecb200_peer_allreduce", _ptr(stats), stats.numel(), c_void_p(peer.bufs_dev), peer.rank,
+                  peer.world, _ptr(peer.seq), _stream(stats))
+    else:
+        dist.all_reduce(stats, group=_GROUPS[handle])
 
 
 def _ptr(t: Optional[Tensor]):
@@ -274,7 +294,7 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
                   _ptr(arg), _ptr(esum), _ptr(stats) if use_batch_stats else None, st)
         if use_batch_stats and group:
             # the one exchange step of the path: [sum e, sum e^2, count] over the ranks
-            dist.all_reduce(stats, group=_GROUPS[group])
+            _allreduce_stats(stats, group)
         _lib.call("ecb200_bn_finalize", _ptr(stats), _ptr(gamma_c), _ptr(beta_c),
                   None if use_batch_stats else _ptr(running_mean),
                   None if use_batch_stats else _ptr(running_var),
@@ -324,7 +344,7 @@ def edgeconv_bwd_op(gout: Optional[Tensor], gout_pm: Optional[Tensor], x: Tensor
                   float(slope), B, N, Co, _ptr(g), _ptr(bstats), st)
         if use_batch_stats and group:
             bglobal = bstats.clone()
-            dist.all_reduce(bglobal, group=_GROUPS[group])
+            _allreduce_stats(bglobal, group)
         else:
             bglobal = bstats
         dgamma = torch.empty(Co, **f32)
@@ -484,7 +504,7 @@ def embed_pool_fwd_op(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor,
         if use_batch_stats:
             _lib.call("ecb200_colstats", _ptr(z), M, E, _ptr(stats), st)
             if group:
-                dist.all_reduce(stats, group=_GROUPS[group])
+                _allreduce_stats(stats, group)
         _lib.call("ecb200_bn_finalize", _ptr(stats), _ptr(gamma_c), _ptr(beta_c),
                   None if use_batch_stats else _ptr(running_mean),
                   None if use_batch_stats else _ptr(running_var),
@@ -516,7 +536,7 @@ def embed_pool_bwd_op(gpool: Tensor, z: Tensor, arg: Tensor, affine: Tensor, sta
                   float(slope), B, N, E, _ptr(bstats), st)
         if use_batch_stats and group:
             bglobal = bstats.clone()
-            dist.all_reduce(bglobal, group=_GROUPS[group])
+            _allreduce_stats(bglobal, group)
         else:
             bglobal = bstats
         dgamma = torch.empty(E, **f32)

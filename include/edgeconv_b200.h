@@ -252,6 +252,19 @@ int ecb200_embed_pool_bwd_dz(const float* z, const float* gpool, const int32_t* 
                              const float* b, const float* mean, const float* c1, const float* c2,
                              float slope, int B, int N, int E, float* dz, void* stream);
 
+/* ---- multi-GPU: the SyncBatchNorm statistics exchange fused into one kernel over NVLink peer
+ * memory (replaces the all_gather / all_reduce of torch's SyncBatchNorm, main_partseg_dist.py:189).
+ * vals[0..n) (fp64, device) <- element-wise sum over the ranks, in rank order, in place.
+ * peer_bufs: DEVICE array of `world` pointers, entry p = rank p's symmetric buffer of
+ * ecb200_peer_buffer_bytes(world) bytes, zero-filled once, mapped into this process (e.g. through
+ * torch.distributed._symmetric_memory); seq_counter: one device uint64 per buffer, zero-filled
+ * once, private to the rank.  Every rank must issue the same sequence of exchanges.  No host
+ * synchronisation; capturable in a CUDA graph. */
+#define ECB200_PEER_MAX_VALUES 4160   /* >= 2*2048+1: [sum | sum sq | count] of up to 2048 channels */
+size_t ecb200_peer_buffer_bytes(int world);
+int ecb200_peer_allreduce(double* vals, int n, void* const* peer_bufs, int rank, int world,
+                          unsigned long long* seq_counter, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
