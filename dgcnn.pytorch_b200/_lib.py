@@ -28,6 +28,7 @@ SIGNATURES = {
     "ecb200_graph_feature": (P, P, I, I, I, I, I, P, P),
     "ecb200_graph_feature_bwd": (P, P, I, I, I, I, I, P, P),
     "ecb200_pack_weight": (P, I, I, I, P, P),
+    "ecb200_prepare_weights": (P, I, I, I, P, P, P, P, P, P),
     "ecb200_point_gemm": (P, P, I, I, I, I, P, P),
     "ecb200_edge_gather": (P, P, P, I, I, I, I, P, P, P, P, P),
     "ecb200_bn_finalize": (P, P, P, P, P, I, F, I, P, P, P, P, P),

@@ -114,6 +114,29 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int Co, int C, i
   }
 }
 
+// pack_weight + the tf32 hi/lo operand halves of Wcat and of Wcat^T in one pass (the forward
+// point GEMM multiplies by Wcat [2Co,C], the backward dx GEMM by Wcat^T [C,2Co])
+__global__ void prepare_weights_kernel(const float* __restrict__ W, int Co, int C, int sub,
+                                       float* __restrict__ Wcat, float* __restrict__ hi,
+                                       float* __restrict__ lo, float* __restrict__ hiT,
+                                       float* __restrict__ loT) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 2 * Co * C) return;
+  int row = e / C, c = e % C;
+  float v;
+  if (row < Co) {
+    v = W[(size_t)row * 2 * C + c];
+  } else {
+    int o = row - Co;
+    float w2 = W[(size_t)o * 2 * C + C + c];
+    v = sub ? w2 - W[(size_t)o * 2 * C + c] : w2;
+  }
+  Wcat[e] = v;
+  const float h = ecb200::tf32_rna(v), l = ecb200::tf32_rna(v - h);
+  if (hi) { hi[e] = h; lo[e] = l; }
+  if (hiT) { hiT[(size_t)c * 2 * Co + row] = h; loT[(size_t)c * 2 * Co + row] = l; }
+}
+
 __global__ void unpack_weight_grad_kernel(const float* __restrict__ dWcat, int Co, int C, int sub,
                                           float* __restrict__ dW) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,6 +175,19 @@ extern "C" int ecb200_unpack_weight_grad(const float* dWcat, int Co, int C, int 
   return ECB200_OK;
 }
 
+extern "C" int ecb200_prepare_weights(const float* W, int Co, int C, int subtract_center, float* Wcat,
+                                      float* hi, float* lo, float* hiT, float* loT, void* stream) {
+  ECB_REQUIRE(W && Wcat, "ecb200_prepare_weights: null pointer");
+  ECB_REQUIRE((hi == nullptr) == (lo == nullptr) && (hiT == nullptr) == (loT == nullptr),
+              "ecb200_prepare_weights: hi/lo (and hiT/loT) come in pairs");
+  ECB_REQUIRE(Co >= 1 && C >= 1, "ecb200_prepare_weights: bad shape Co=%d C=%d", Co, C);
+  const int n = 2 * Co * C;
+  prepare_weights_kernel<<<ecb200::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      W, Co, C, subtract_center, Wcat, hi, lo, hiT, loT);
+  ECB_LAUNCH_CHECK("prepare_weights_kernel");
+  return ECB200_OK;
+}
+
 extern "C" int ecb200_point_gemm(const float* x, const float* Wcat, int B, int C, int N, int Co2,
                                  float* Y, void* stream) {
   ECB_REQUIRE(x && Wcat && Y, "ecb200_point_gemm: null pointer");
@@ -180,12 +216,52 @@ extern "C" int ecb200_gemm_dx(const float* dY, const float* Wcat, int B, int C, 
   return ECB200_OK;
 }
 
+// dWcat for a handful of input channels (the xyz layer, C = 3): thread = output row o, a block
+// streams a slab of points; dY rows are read coalesced, the C coordinates of a point are a
+// broadcast load.  One atomic per (block, o, c).
+template <int CC>
+__global__ void __launch_bounds__(256)
+gemm_dw_smallc_kernel(const float* __restrict__ dY, const float* __restrict__ x, int C, int N, int Co2,
+                      long long M, long long slab, float* __restrict__ dWcat) {
+  const long long m0 = (long long)blockIdx.x * slab;
+  const long long m1 = m0 + slab < M ? m0 + slab : M;
+  for (int o = threadIdx.x; o < Co2; o += blockDim.x) {
+    float acc[CC];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) acc[c] = 0.f;
+#pragma unroll 4
+    for (long long m = m0; m < m1; ++m) {
+      const long long b = m / N;
+      const int n = (int)(m - b * N);
+      const float dy = dY[m * Co2 + o];
+#pragma unroll
+      for (int c = 0; c < CC; ++c)
+        if (c < C) acc[c] = fmaf(dy, __ldg(x + ((size_t)b * C + c) * N + n), acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < CC; ++c)
+      if (c < C) atomicAdd(dWcat + (size_t)o * C + c, acc[c]);
+  }
+}
+
 extern "C" int ecb200_gemm_dw(const float* dY, const float* x, int B, int C, int N, int Co2,
                               float* dWcat, void* stream) {
   ECB_REQUIRE(dY && x && dWcat, "ecb200_gemm_dw: null pointer");
   ECB_REQUIRE(B >= 1 && C >= 1 && N >= 1 && Co2 >= 2, "ecb200_gemm_dw: bad shape");
   long long M = (long long)B * N;
   ECB_CUDA(cudaMemsetAsync(dWcat, 0, sizeof(float) * (size_t)Co2 * C, (cudaStream_t)stream));
+  if (C <= 4) {
+    // few blocks: every block ends with one atomic per (o, c) on the same 2Co*C addresses
+    long long blocks = 2LL * ecb200::kNumSMs;
+    long long slab = ecb200::ceil_div64(M, blocks);
+    if (slab < 16) slab = 16;
+    blocks = ecb200::ceil_div64(M, slab);
+    const int threads = Co2 >= 256 ? 256 : (Co2 + 31) / 32 * 32;
+    gemm_dw_smallc_kernel<4><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(dY, x, C, N, Co2, M, slab,
+                                                                                 dWcat);
+    ECB_LAUNCH_CHECK("gemm_dw_smallc_kernel");
+    return ECB200_OK;
+  }
   // out[o,c] = sum_m dY[m,o] * X^T[m,c]:  A(o,m) = dY[m*Co2+o] (o contiguous),
   // B(m,c) = x[b,c,n] (m contiguous); the M-long reduction is cut into slabs.
   const int tiles = ecb200::ceil_div(Co2, BM) * ecb200::ceil_div(C, BN);

@@ -251,7 +251,7 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
                     use_batch_stats: bool, eps: float, slope: float, subtract_center: bool,
                     group: int, save_for_bwd: bool, xhi: Optional[Tensor],
                     xlo: Optional[Tensor], emit_pm: bool) -> List[Tensor]:
-    """Returns [out, out_pm, sel, arg, esum, Y, Wcat, affine, stats]; ``out_pm`` [B*N, Co] is the
+    """Returns [out, out_pm, sel, arg, esum, Y, Wcat, affine, stats, wsplit]; ``out_pm`` [B*N, Co] is the
     same output point-major (rows of channels; empty unless ``emit_pm``); ``affine`` is [4,Co] =
     (mean, invstd, a, b).  Everything after ``out_pm`` exists for the backward pass."""
     _check_cuda_f32("x", x, 3)
@@ -281,14 +281,19 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
         mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * Co * r) for r in range(4))
         out = torch.empty(B, Co, N, **f32)
         out_pm = torch.empty(M, Co, **f32) if emit_pm else None
-        _lib.call("ecb200_pack_weight", _ptr(w), Co, C, int(subtract_center), _ptr(Wcat), st)
         if xhi is not None and xlo is not None and point_gemm_uses_tensor_cores(C):
-            # the per-point GEMM on the tensor cores, from the operands the kNN already made
-            wsplit = torch.empty(2, 2 * Co, C, **f32)
-            _lib.call("ecb200_split_rows_tf32", _ptr(Wcat), 2 * Co * C, _ptr(wsplit[0]), _ptr(wsplit[1]), st)
+            # the per-point GEMM on the tensor cores, from the operands the kNN already made; one
+            # kernel packs Wcat and produces its tf32 halves for this GEMM and (transposed) for
+            # the backward dx GEMM
+            wsplit = torch.empty(4, 2 * Co * C, **f32)     # Wcat hi, lo [2Co,C]; Wcat^T hi, lo [C,2Co]
+            _lib.call("ecb200_prepare_weights", _ptr(w), Co, C, int(subtract_center), _ptr(Wcat),
+                      _ptr(wsplit[0]), _ptr(wsplit[1]), _ptr(wsplit[2]) if save_for_bwd else None,
+                      _ptr(wsplit[3]) if save_for_bwd else None, st)
             _lib.call("ecb200_point_gemm_tc", _ptr(xhi), _ptr(xlo), _ptr(wsplit[0]), _ptr(wsplit[1]), M, C,
                       2 * Co, _ptr(Y), st)
         else:
+            wsplit = None
+            _lib.call("ecb200_pack_weight", _ptr(w), Co, C, int(subtract_center), _ptr(Wcat), st)
             _lib.call("ecb200_point_gemm", _ptr(x), _ptr(Wcat), B, C, N, 2 * Co, _ptr(Y), st)
         _lib.call("ecb200_edge_gather", _ptr(Y), _ptr(idx), _ptr(gamma_c), B, N, k, Co, _ptr(sel),
                   _ptr(arg), _ptr(esum), _ptr(stats) if use_batch_stats else None, st)
@@ -305,7 +310,9 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
         esum = sel.new_empty(0)
     if out_pm is None:
         out_pm = sel.new_empty(0)
-    return [out, out_pm, sel, arg, esum, Y, Wcat, affine, stats]
+    if wsplit is None:
+        wsplit = sel.new_empty(0)
+    return [out, out_pm, sel, arg, esum, Y, Wcat, affine, stats, wsplit]
 
 
 @edgeconv_fwd_op.register_fake
@@ -317,30 +324,38 @@ def _(x, idx, weight, gamma, beta, running_mean, running_var, use_batch_stats, e
     f = x.new_empty
     return [f((B, Co, N)), f((M, Co)) if emit_pm else f((0,)), f((M, Co)), f((M, Co), dtype=torch.uint8),
             f((M, Co)) if save_for_bwd else f((0,)), f((M, 2 * Co)), f((2 * Co, C)),
-            f((4, Co)), f((2 * Co + 1,), dtype=torch.float64)]
+            f((4, Co)), f((2 * Co + 1,), dtype=torch.float64),
+            f((4, 2 * Co * C)) if (xhi is not None and xlo is not None and point_gemm_uses_tensor_cores(C))
+            else f((0,))]
 
 
 @torch.library.custom_op("edgeconv_b200::edgeconv_bwd", mutates_args=(), device_types="cuda")
 def edgeconv_bwd_op(gout: Optional[Tensor], gout_pm: Optional[Tensor], x: Tensor, idx: Tensor, sel: Tensor,
-                    arg: Tensor, esum: Tensor,
+                    arg: Tensor, esum: Tensor, wsplit: Tensor,
                     Y: Tensor, Wcat: Tensor, affine: Tensor, stats: Tensor, use_batch_stats: bool,
                     slope: float, subtract_center: bool, group: int, xhi: Optional[Tensor],
-                    xlo: Optional[Tensor]) -> List[Tensor]:
-    """-> [dx [B,C,N], dW [Co,2C], dgamma [Co], dbeta [Co]]"""
+                    xlo: Optional[Tensor], need_dx: bool) -> List[Tensor]:
+    """-> [dx [B,C,N] (empty unless need_dx), dW [Co,2C], dgamma [Co], dbeta [Co]]"""
     B, C, N = x.shape
     k = idx.shape[-1]
     Co = sel.shape[1]
     M = B * N
     dev = x.device
     gout = None if gout is None else gout.contiguous().float()
-    gout_pm = None if gout_pm is None else gout_pm.contiguous().float()
+    ld_pm = Co
+    if gout_pm is not None:
+        gout_pm = gout_pm.float()
+        if gout_pm.dim() == 2 and gout_pm.stride(1) == 1 and gout_pm.stride(0) >= Co:
+            ld_pm = gout_pm.stride(0)      # e.g. a column slice of the concat's gradient: read in place
+        else:
+            gout_pm = gout_pm.contiguous()
     with torch.cuda.device(dev):
         st = _stream(x)
         f32 = dict(device=dev, dtype=torch.float32)
         g = torch.empty(M, Co, **f32)
         bstats = torch.zeros(2 * Co, device=dev, dtype=torch.float64)
         mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * Co * r) for r in range(4))
-        _lib.call("ecb200_bwd_prep", _ptr(gout), _ptr(gout_pm), Co, _ptr(sel), a, b, mean, invstd,
+        _lib.call("ecb200_bwd_prep", _ptr(gout), _ptr(gout_pm), ld_pm, _ptr(sel), a, b, mean, invstd,
                   float(slope), B, N, Co, _ptr(g), _ptr(bstats), st)
         if use_batch_stats and group:
             bglobal = bstats.clone()
@@ -360,7 +375,7 @@ def edgeconv_bwd_op(gout: Optional[Tensor], gout_pm: Optional[Tensor], x: Tensor
             src = torch.empty(M * k, device=dev, dtype=torch.int32)
             cursor = torch.empty(M, device=dev, dtype=torch.int32)
             _lib.call("ecb200_reverse_graph", _ptr(idx), B, N, k, _ptr(rowptr), _ptr(src), _ptr(cursor), st)
-        dx = torch.empty(B, C, N, **f32)
+        dx = torch.empty(B, C, N, **f32) if need_dx else torch.empty(0, **f32)
         dWcat = torch.empty(2 * Co, C, **f32)
         dW = torch.empty(Co, 2 * C, **f32)
         if xhi is not None and xlo is not None and bwd_gemm_uses_tensor_cores(C, Co):
@@ -369,14 +384,18 @@ def edgeconv_bwd_op(gout: Optional[Tensor], gout_pm: Optional[Tensor], x: Tensor
             # the dense BatchNorm terms are added and the sum is split
             dYs = torch.empty(2, M, 2 * Co, **f32)
             dU = torch.zeros(M, Co, **f32)
-            wT = torch.empty(2, C, 2 * Co, **f32)
+            if wsplit.numel() == 4 * 2 * Co * C:
+                wT = wsplit.view(4, C, 2 * Co)[2:]           # Wcat^T hi/lo from the forward
+            else:
+                wT = torch.empty(2, C, 2 * Co, **f32)
+                _lib.call("ecb200_transpose_split_tf32", _ptr(Wcat), 2 * Co, C, _ptr(wT[0]), _ptr(wT[1]), st)
             _lib.call("ecb200_bwd_scatter", _ptr(g), _ptr(esum), _ptr(arg), _ptr(idx), a, mean, c1, c2,
                       B, N, k, Co, None, _ptr(dU), _ptr(dYs[0]), _ptr(dYs[1]), st)
             _lib.call("ecb200_bwd_dense", _ptr(Y), _ptr(rowptr), _ptr(src), mean, c1, c2,
                       int(use_batch_stats), B, N, Co, None, _ptr(dU), _ptr(dYs[0]), _ptr(dYs[1]), st)
-            _lib.call("ecb200_transpose_split_tf32", _ptr(Wcat), 2 * Co, C, _ptr(wT[0]), _ptr(wT[1]), st)
-            _lib.call("ecb200_gemm_dx_tc", _ptr(dYs[0]), _ptr(dYs[1]), _ptr(wT[0]), _ptr(wT[1]), B, C, N,
-                      2 * Co, _ptr(dx), st)
+            if need_dx:
+                _lib.call("ecb200_gemm_dx_tc", _ptr(dYs[0]), _ptr(dYs[1]), _ptr(wT[0]), _ptr(wT[1]), B, C, N,
+                          2 * Co, _ptr(dx), st)
             _lib.call("ecb200_gemm_dw_tc", _ptr(dYs[0]), _ptr(dYs[1]), _ptr(xhi), _ptr(xlo), M, C, 2 * Co,
                       _ptr(dWcat), st)
         else:
@@ -385,30 +404,32 @@ def edgeconv_bwd_op(gout: Optional[Tensor], gout_pm: Optional[Tensor], x: Tensor
                       int(use_batch_stats), B, N, Co, _ptr(dY), None, None, None, st)
             _lib.call("ecb200_bwd_scatter", _ptr(g), _ptr(esum), _ptr(arg), _ptr(idx), a, mean,
                       c1, c2, B, N, k, Co, _ptr(dY), None, None, None, st)
-            _lib.call("ecb200_gemm_dx", _ptr(dY), _ptr(Wcat), B, C, N, 2 * Co, _ptr(dx), st)
+            if need_dx:
+                _lib.call("ecb200_gemm_dx", _ptr(dY), _ptr(Wcat), B, C, N, 2 * Co, _ptr(dx), st)
             _lib.call("ecb200_gemm_dw", _ptr(dY), _ptr(x), B, C, N, 2 * Co, _ptr(dWcat), st)
         _lib.call("ecb200_unpack_weight_grad", _ptr(dWcat), Co, C, int(subtract_center), _ptr(dW), st)
     return [dx, dW, dgamma, dbeta]
 
 
 @edgeconv_bwd_op.register_fake
-def _(gout, gout_pm, x, idx, sel, arg, esum, Y, Wcat, affine, stats, use_batch_stats, slope,
-      subtract_center, group, xhi, xlo):
+def _(gout, gout_pm, x, idx, sel, arg, esum, wsplit, Y, Wcat, affine, stats, use_batch_stats, slope,
+      subtract_center, group, xhi, xlo, need_dx):
     B, C, N = x.shape
     Co = sel.shape[1]
     f = x.new_empty
-    return [f((B, C, N)), f((Co, 2 * C)), f((Co,)), f((Co,))]
+    return [f((B, C, N)) if need_dx else f((0,)), f((Co, 2 * C)), f((Co,)), f((Co,))]
 
 
 def _ec_setup(ctx, inputs, output):
     (x, idx, weight, gamma, beta, _rm, _rv, use_batch_stats, _eps, slope, subtract_center, group,
      save_for_bwd, _xhi, _xlo, _emit_pm) = inputs
-    out, out_pm, sel, arg, esum, Y, Wcat, affine, stats = output
+    out, out_pm, sel, arg, esum, Y, Wcat, affine, stats, wsplit = output
     if not save_for_bwd:
         raise RuntimeError("edgeconv_b200: forward ran with save_for_bwd=False but a gradient "
                            "is required")
-    ctx.save_for_backward(x, idx, sel, arg, esum, Y, Wcat, affine, stats, _xhi, _xlo)
+    ctx.save_for_backward(x, idx, sel, arg, esum, Y, Wcat, affine, stats, _xhi, _xlo, wsplit)
     ctx.cfg = (use_batch_stats, slope, subtract_center, group)
+    ctx.need_dx = bool(x.requires_grad)
     ctx.wshape = tuple(weight.shape)
     ctx.set_materialize_grads(False)
 
@@ -418,11 +439,12 @@ def _ec_backward(ctx, grads):
     n_in = 16
     if gout is None and gout_pm is None:
         return (None,) * n_in
-    x, idx, sel, arg, esum, Y, Wcat, affine, stats, xhi, xlo = ctx.saved_tensors
+    x, idx, sel, arg, esum, Y, Wcat, affine, stats, xhi, xlo, wsplit = ctx.saved_tensors
     use_batch_stats, slope, subtract_center, group = ctx.cfg
-    dx, dW, dgamma, dbeta = edgeconv_bwd_op(gout, gout_pm, x, idx, sel, arg, esum, Y, Wcat, affine, stats,
-                                            use_batch_stats, slope, subtract_center, group, xhi, xlo)
-    return (dx, None, dW.view(ctx.wshape), dgamma, dbeta) + (None,) * (n_in - 5)
+    dx, dW, dgamma, dbeta = edgeconv_bwd_op(gout, gout_pm, x, idx, sel, arg, esum, wsplit, Y, Wcat, affine, stats,
+                                            use_batch_stats, slope, subtract_center, group, xhi, xlo,
+                                            ctx.need_dx)
+    return (dx if ctx.need_dx else None, None, dW.view(ctx.wshape), dgamma, dbeta) + (None,) * (n_in - 5)
 
 
 edgeconv_fwd_op.register_autograd(_ec_backward, setup_context=_ec_setup)
@@ -470,7 +492,7 @@ def edgeconv(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor
                           float(eps), float(slope), bool(subtract_center), int(group), bool(need_grad),
                           xhi, xlo, bool(return_point_major))
     if update_running:
-        bn_update_running_op(res[-1].detach(), running_mean, running_var, num_batches_tracked, mom)
+        bn_update_running_op(res[8].detach(), running_mean, running_var, num_batches_tracked, mom)
     if return_point_major:
         return res[0], res[1]          # [B,Co,N] and the same values as [B*N, Co]
     return res[0]

@@ -118,6 +118,12 @@ int ecb200_graph_feature_bwd(const float* gout, const int32_t* idx, int B, int C
 int ecb200_pack_weight(const float* W, int Co, int C, int subtract_center, float* Wcat,
                        void* stream);
 
+/* ecb200_pack_weight plus, in the same pass, the tf32 hi/lo halves of Wcat ([2Co,C]; operands of
+ * ecb200_point_gemm_tc) and of Wcat^T ([C,2Co]; operands of ecb200_gemm_dx_tc).  Either pair may
+ * be NULL. */
+int ecb200_prepare_weights(const float* W, int Co, int C, int subtract_center, float* Wcat,
+                           float* hi, float* lo, float* hiT, float* loT, void* stream);
+
 /* Y[M,2Co] = [U | V],  U = x^T W1^T,  V = x^T W2'^T : the one dense per-point
  * GEMM that replaces the k-fold 1x1 convolution over [B,2C,N,k]. */
 int ecb200_point_gemm(const float* x, const float* Wcat, int B, int C, int N, int Co2,
