@@ -216,31 +216,53 @@ extern "C" int ecb200_gemm_dx(const float* dY, const float* Wcat, int B, int C, 
   return ECB200_OK;
 }
 
-// dWcat for a handful of input channels (the xyz layer, C = 3): thread = output row o, a block
-// streams a slab of points; dY rows are read coalesced, the C coordinates of a point are a
-// broadcast load.  One atomic per (block, o, c).
+// dWcat for a handful of input channels (the xyz layer, C = 3).  A block of 1024 threads =
+// (1024 / 2Co) point lanes x 2Co output rows streams a slab of points: dY rows are read
+// coalesced, the C coordinates of a point are a broadcast load.  The lanes are summed in shared
+// memory and the block issues ONE atomic per (o, c): atomics onto the same few cache lines
+// serialise in the L2, so there are only ~40 blocks.
 template <int CC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 gemm_dw_smallc_kernel(const float* __restrict__ dY, const float* __restrict__ x, int C, int N, int Co2,
                       long long M, long long slab, float* __restrict__ dWcat) {
+  extern __shared__ float red[];  // [lanes][Co2][CC]
+  const int lanes = blockDim.x / Co2;
+  const int o = threadIdx.x % Co2, lane = threadIdx.x / Co2;
   const long long m0 = (long long)blockIdx.x * slab;
   const long long m1 = m0 + slab < M ? m0 + slab : M;
-  for (int o = threadIdx.x; o < Co2; o += blockDim.x) {
-    float acc[CC];
+  float acc[CC];
 #pragma unroll
-    for (int c = 0; c < CC; ++c) acc[c] = 0.f;
-#pragma unroll 4
-    for (long long m = m0; m < m1; ++m) {
-      const long long b = m / N;
-      const int n = (int)(m - b * N);
-      const float dy = dY[m * Co2 + o];
+  for (int c = 0; c < CC; ++c) acc[c] = 0.f;
+  if (lane < lanes) {
+    // 8 independent (dY, x) load groups in flight per thread: the loop is latency-bound
+    for (long long mb = m0 + lane; mb < m1; mb += 8LL * lanes) {
+      float dy[8], xv[8][CC];
 #pragma unroll
-      for (int c = 0; c < CC; ++c)
-        if (c < C) acc[c] = fmaf(dy, __ldg(x + ((size_t)b * C + c) * N + n), acc[c]);
+      for (int u = 0; u < 8; ++u) {
+        const long long m = mb + (long long)u * lanes;
+        const bool ok = m < m1;
+        const unsigned mm = ok ? (unsigned)m : (unsigned)m0;   // M < 2^31 (checked by the caller)
+        const unsigned b = mm / (unsigned)N, n = mm - b * (unsigned)N;
+        dy[u] = ok ? dY[(size_t)mm * Co2 + o] : 0.f;
+#pragma unroll
+        for (int c = 0; c < CC; ++c) xv[u][c] = c < C ? __ldg(x + ((size_t)b * C + c) * N + n) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int c = 0; c < CC; ++c) acc[c] = fmaf(dy[u], xv[u][c], acc[c]);
     }
 #pragma unroll
-    for (int c = 0; c < CC; ++c)
-      if (c < C) atomicAdd(dWcat + (size_t)o * C + c, acc[c]);
+    for (int c = 0; c < CC; ++c) red[((size_t)lane * Co2 + o) * CC + c] = acc[c];
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      float t = 0.f;
+      for (int l = 0; l < lanes; ++l) t += red[((size_t)l * Co2 + o) * CC + c];
+      if (c < C) atomicAdd(dWcat + (size_t)o * C + c, t);
+    }
   }
 }
 
@@ -250,15 +272,16 @@ extern "C" int ecb200_gemm_dw(const float* dY, const float* x, int B, int C, int
   ECB_REQUIRE(B >= 1 && C >= 1 && N >= 1 && Co2 >= 2, "ecb200_gemm_dw: bad shape");
   long long M = (long long)B * N;
   ECB_CUDA(cudaMemsetAsync(dWcat, 0, sizeof(float) * (size_t)Co2 * C, (cudaStream_t)stream));
-  if (C <= 4) {
-    // few blocks: every block ends with one atomic per (o, c) on the same 2Co*C addresses
-    long long blocks = 2LL * ecb200::kNumSMs;
+  if (C <= 4 && Co2 <= 1024 && M < (1LL << 31)) {
+    const int lanes = 1024 / Co2;
+    const int threads = lanes * Co2;
+    long long blocks = 40;
     long long slab = ecb200::ceil_div64(M, blocks);
-    if (slab < 16) slab = 16;
+    if (slab < lanes) slab = lanes;
     blocks = ecb200::ceil_div64(M, slab);
-    const int threads = Co2 >= 256 ? 256 : (Co2 + 31) / 32 * 32;
-    gemm_dw_smallc_kernel<4><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(dY, x, C, N, Co2, M, slab,
-                                                                                 dWcat);
+    const size_t smem = sizeof(float) * (size_t)lanes * Co2 * 4;
+    gemm_dw_smallc_kernel<4><<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(dY, x, C, N, Co2, M,
+                                                                                       slab, dWcat);
     ECB_LAUNCH_CHECK("gemm_dw_smallc_kernel");
     return ECB200_OK;
   }

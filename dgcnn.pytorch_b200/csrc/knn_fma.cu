@@ -147,17 +147,26 @@ knn_fma_kernel(const float* __restrict__ x, const float* __restrict__ xx, int C,
 constexpr int XR = 32;        // rows per CTA
 constexpr int XT = 4;         // threads per row
 constexpr int XNT = XR * XT;  // 128 threads
-constexpr int XCAP_MIN = 32;  // survivor slots per thread (expected use: ~6 at k=20, ~12 at k=40)
+constexpr int XCAP_MIN = 24;  // survivor slots per thread (expected use: ~6 at k=20, ~12 at k=40); >= NB/2 (bins alias them)
 constexpr int XTILE = 4096;   // candidates staged at a time (64 KB)
 using XSurv = Survivors<XNT>;
+
+__device__ __forceinline__ uint64_t raw_to_key(uint64_t raw) {
+  return make_key(__uint_as_float((uint32_t)(raw >> 32)), (int)(uint32_t)raw);
+}
+__device__ __forceinline__ uint64_t key_to_raw(uint64_t key) {
+  return ((uint64_t)__float_as_uint(key_score(key)) << 32) | key_index(key);
+}
 
 template <int C>
 __global__ void __launch_bounds__(XNT)
 knn_xyz_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int k, int cap,
                int sorted, int32_t* __restrict__ idx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sbin = reinterpret_cast<float*>(smem_raw + XSurv::smem_bytes(cap));  // [NB][XNT]
-  int* scnt = reinterpret_cast<int*>(sbin + NB * XNT);                      // [XNT]
+  // the sorted bin maxima [NB][XNT] are only needed between the passes: they share the memory of
+  // the survivor lists (cap >= 16 slots of 8 bytes per thread >= NB floats per thread)
+  float* sbin = reinterpret_cast<float*>(smem_raw);
+  int* scnt = reinterpret_cast<int*>(smem_raw + XSurv::smem_bytes(cap));    // [XNT]
   float4* cand = reinterpret_cast<float4*>(scnt + XNT);                     // [<= XTILE]
 
   const int b = blockIdx.y;
@@ -209,8 +218,10 @@ knn_xyz_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N,
   // -3e38 floor: padding candidates score -inf and must never pass, even when the cloud has
   // fewer than k non-empty bins
   const float tau = fmaxf(kth_of_sorted_columns<XT>(sbin, r, XR, XNT, k), -3.0e38f);
+  __syncthreads();  // every thread has read the bins: their memory now holds the survivor lists
 
-  // ---- pass B: survivors
+  // ---- pass B: survivors, appended as raw (score bits, j) words -- the ordered key is only
+  //      built for the few entries that survive, after the sweep
   XSurv sv;
   sv.init(smem_raw, tid, cap, tau);
   for (int t0 = 0; t0 < N; t0 += XTILE) {
@@ -218,12 +229,23 @@ knn_xyz_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N,
     for (int j0 = h * NB; j0 < padded; j0 += XNT) {
 #pragma unroll
       for (int g = 0; g < NB / 8; ++g) {
-        sv.guard(k, 8);
+        if (sv.cnt > sv.cap - 8) {  // rare: keep the thread's own best k (works on ordered keys)
+          for (int e = 0; e < sv.cnt; ++e) sv.buf[e * XNT] = raw_to_key(sv.buf[e * XNT]);
+          sv.shrink_to(k);
+          for (int e = 0; e < sv.cnt; ++e) sv.buf[e * XNT] = key_to_raw(sv.buf[e * XNT]);
+        }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sv.offer(score(cand[j0 + g * 8 + u]), t0 + j0 + g * 8 + u);
+        for (int u = 0; u < 8; ++u) {
+          const float sc = score(cand[j0 + g * 8 + u]);
+          if (sc >= sv.thr) {
+            sv.buf[sv.cnt * XNT] = ((uint64_t)__float_as_uint(sc) << 32) | (uint32_t)(t0 + j0 + g * 8 + u);
+            ++sv.cnt;
+          }
+        }
       }
     }
   }
+  for (int e = 0; e < sv.cnt; ++e) sv.buf[e * XNT] = raw_to_key(sv.buf[e * XNT]);
   scnt[tid] = sv.cnt;
   __syncthreads();
 
@@ -278,11 +300,9 @@ extern "C" int ecb200_knn(const float* x, const float* xx, int B, int C, int N, 
   if (C <= 3) {
     const int staged = N < XTILE ? (N + XNT - 1) / XNT * XNT : XTILE;
     const int cap = XSurv::capacity(k, 8, XCAP_MIN);
-    const size_t smem = XSurv::smem_bytes(cap) + (size_t)NB * XNT * sizeof(float) + XNT * sizeof(int) +
-                        (size_t)staged * sizeof(float4);
+    const size_t smem = XSurv::smem_bytes(cap) + XNT * sizeof(int) + (size_t)staged * sizeof(float4);
     const size_t smem_max = XSurv::smem_bytes(XSurv::capacity(ECB200_MAX_K, 8, XCAP_MIN)) +
-                            (size_t)NB * XNT * sizeof(float) + XNT * sizeof(int) +
-                            (size_t)XTILE * sizeof(float4);
+                            XNT * sizeof(int) + (size_t)XTILE * sizeof(float4);
     static thread_local bool seen_xyz[ecb200::kMaxDevices] = {};
     if (ecb200::first_use_on_device(seen_xyz)) {
       ECB_CUDA(cudaFuncSetAttribute(knn_xyz_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
