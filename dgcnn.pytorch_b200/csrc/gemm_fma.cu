@@ -224,37 +224,36 @@ extern "C" int ecb200_gemm_dx(const float* dY, const float* Wcat, int B, int C, 
 template <int CC>
 __global__ void __launch_bounds__(1024)
 gemm_dw_smallc_kernel(const float* __restrict__ dY, const float* __restrict__ x, int C, int N, int Co2,
-                      long long M, long long slab, float* __restrict__ dWcat) {
+                      int slab, float* __restrict__ dWcat) {
   extern __shared__ float red[];  // [lanes][Co2][CC]
   const int lanes = blockDim.x / Co2;
   const int o = threadIdx.x % Co2, lane = threadIdx.x / Co2;
-  const long long m0 = (long long)blockIdx.x * slab;
-  const long long m1 = m0 + slab < M ? m0 + slab : M;
+  const int bb = blockIdx.y;                    // one cloud per block row: no index division
+  const int n0 = blockIdx.x * slab, n1 = min(N, n0 + slab);
+  const float* dyb = dY + (size_t)bb * N * Co2 + o;
+  const float* xb = x + (size_t)bb * C * N;
   float acc[CC];
 #pragma unroll
   for (int c = 0; c < CC; ++c) acc[c] = 0.f;
-  if (lane < lanes) {
-    // 8 independent (dY, x) load groups in flight per thread: the loop is latency-bound
-    for (long long mb = m0 + lane; mb < m1; mb += 8LL * lanes) {
-      float dy[8], xv[8][CC];
+  // 8 independent (dY, x) load groups in flight per thread: the loop is latency-bound
+  for (int nb = n0 + lane; nb < n1; nb += 8 * lanes) {
+    float dy[8], xv[8][CC];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const long long m = mb + (long long)u * lanes;
-        const bool ok = m < m1;
-        const unsigned mm = ok ? (unsigned)m : (unsigned)m0;   // M < 2^31 (checked by the caller)
-        const unsigned b = mm / (unsigned)N, n = mm - b * (unsigned)N;
-        dy[u] = ok ? dY[(size_t)mm * Co2 + o] : 0.f;
+    for (int u = 0; u < 8; ++u) {
+      const int n = nb + u * lanes;
+      const bool ok = n < n1;
+      const int nn = ok ? n : n0;
+      dy[u] = ok ? dyb[(size_t)nn * Co2] : 0.f;
 #pragma unroll
-        for (int c = 0; c < CC; ++c) xv[u][c] = c < C ? __ldg(x + ((size_t)b * C + c) * N + n) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int c = 0; c < CC; ++c) acc[c] = fmaf(dy[u], xv[u][c], acc[c]);
+      for (int c = 0; c < CC; ++c) xv[u][c] = c < C ? __ldg(xb + (size_t)c * N + nn) : 0.f;
     }
 #pragma unroll
-    for (int c = 0; c < CC; ++c) red[((size_t)lane * Co2 + o) * CC + c] = acc[c];
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int c = 0; c < CC; ++c) acc[c] = fmaf(dy[u], xv[u][c], acc[c]);
   }
+#pragma unroll
+  for (int c = 0; c < CC; ++c) red[((size_t)lane * Co2 + o) * CC + c] = acc[c];
   __syncthreads();
   if (lane == 0) {
 #pragma unroll
@@ -272,16 +271,17 @@ extern "C" int ecb200_gemm_dw(const float* dY, const float* x, int B, int C, int
   ECB_REQUIRE(B >= 1 && C >= 1 && N >= 1 && Co2 >= 2, "ecb200_gemm_dw: bad shape");
   long long M = (long long)B * N;
   ECB_CUDA(cudaMemsetAsync(dWcat, 0, sizeof(float) * (size_t)Co2 * C, (cudaStream_t)stream));
-  if (C <= 4 && Co2 <= 1024 && M < (1LL << 31)) {
+  if (C <= 4 && Co2 <= 1024 && B <= 65535) {
     const int lanes = 1024 / Co2;
     const int threads = lanes * Co2;
-    long long blocks = 40;
-    long long slab = ecb200::ceil_div64(M, blocks);
-    if (slab < lanes) slab = lanes;
-    blocks = ecb200::ceil_div64(M, slab);
+    // about one block per SM: every block ends with one atomic per (o, c) on the same few lines
+    int per_cloud = ecb200::ceil_div(ecb200::kNumSMs, B);
+    int slab = ecb200::ceil_div(N, per_cloud);
+    if (slab < 8 * lanes) slab = 8 * lanes;
+    per_cloud = ecb200::ceil_div(N, slab);
     const size_t smem = sizeof(float) * (size_t)lanes * Co2 * 4;
-    gemm_dw_smallc_kernel<4><<<(unsigned)blocks, threads, smem, (cudaStream_t)stream>>>(dY, x, C, N, Co2, M,
-                                                                                       slab, dWcat);
+    gemm_dw_smallc_kernel<4><<<dim3(per_cloud, B), threads, smem, (cudaStream_t)stream>>>(dY, x, C, N, Co2,
+                                                                                         slab, dWcat);
     ECB_LAUNCH_CHECK("gemm_dw_smallc_kernel");
     return ECB200_OK;
   }
