@@ -54,7 +54,7 @@ SIGNATURES = {
 
 # kernels each entry point enqueues (memsets are not counted)
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
-KERNELS_PER_CALL["ecb200_reverse_graph"] = 3
+KERNELS_PER_CALL["ecb200_reverse_graph"] = 1      # one CTA per cloud (3 kernels only when N counters exceed shared memory)
 
 # entry points that do not return an error code
 PLAIN = {"ecb200_version": 0, "ecb200_last_error": 0, "ecb200_knn_tc_workspace_bytes": 3,

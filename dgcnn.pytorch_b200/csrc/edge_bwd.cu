@@ -139,6 +139,87 @@ __global__ void rev_fill_kernel(const int32_t* __restrict__ idx, const int32_t* 
   src[rowptr[dst] + pos] = (int32_t)(e / k);
 }
 
+// Shared-memory reverse graph: CTA (s, b) owns the destination points [lo, hi) of cloud b.  It
+// reads the cloud's whole neighbour list twice (L2-resident): once to histogram the in-degrees of
+// its destinations (shared-memory atomics) and to count the edges that go to smaller
+// destinations (its global base offset), once to fill.  Replaces the count / scan / fill triple
+// (global atomics, three launches and a memset) whenever the counters fit shared memory.
+__global__ void __launch_bounds__(1024)
+rev_cloud_kernel(const int32_t* __restrict__ idx, int N, int k, long long M, int span,
+                 int32_t* __restrict__ rowptr, int32_t* __restrict__ src) {
+  extern __shared__ int sh[];          // [span] degree -> cursor, [span] exclusive offsets
+  int* deg = sh;
+  int* off = sh + span;
+  __shared__ int wsum[32];
+  __shared__ int below_s;
+  const int bb = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int lo = blockIdx.x * span, hi = min(N, lo + span), cnt = hi - lo;
+  const int E = N * k;
+  const int32_t* ib = idx + (size_t)bb * E;
+  for (int i = tid; i < cnt; i += blockDim.x) deg[i] = 0;
+  if (tid == 0) below_s = 0;
+  __syncthreads();
+  int below = 0;
+  for (int i = tid; i < N; i += blockDim.x) {   // thread = source point: no index division
+    const int32_t* row = ib + (size_t)i * k;
+#pragma unroll 4
+    for (int j = 0; j < k; ++j) {
+      const int d = row[j];
+      if (d < lo) ++below;
+      else if (d < hi) atomicAdd(&deg[d - lo], 1);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+  if (lane == 0 && below) atomicAdd(&below_s, below);
+  __syncthreads();
+  // exclusive scan of deg[0..cnt): each thread owns a contiguous chunk
+  const int per = (cnt + blockDim.x - 1) / blockDim.x;
+  const int beg = min(cnt, tid * per), end = min(cnt, beg + per);
+  int s = 0;
+  for (int i = beg; i < end; ++i) s += deg[i];
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int v = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    wsum[lane] = v;
+  }
+  __syncthreads();
+  const int gbase = (int)((long long)bb * E) + below_s;   // global offset of destination `lo`
+  int run = (inc - s) + (w > 0 ? wsum[w - 1] : 0);
+  for (int i = beg; i < end; ++i) {
+    off[i] = run;
+    rowptr[(size_t)bb * N + lo + i] = gbase + run;
+    run += deg[i];
+  }
+  if (bb == (int)gridDim.y - 1 && blockIdx.x == gridDim.x - 1 && tid == 0) rowptr[M] = (int32_t)(M * k);
+  __syncthreads();
+  // fill: deg[] now counts down as the cursor of each destination row
+  for (int i = tid; i < N; i += blockDim.x) {
+    const int32_t* row = ib + (size_t)i * k;
+    const int32_t me = (int32_t)((long long)bb * N + i);
+#pragma unroll 4
+    for (int j = 0; j < k; ++j) {
+      const int d = row[j];
+      if (d >= lo && d < hi) {
+        const int pos = atomicSub(&deg[d - lo], 1) - 1;
+        src[gbase + off[d - lo] + pos] = me;
+      }
+    }
+  }
+}
+
 // ---- dense BatchNorm terms of dU through the reverse graph ---------------------------
 template <int LPP>
 __global__ void __launch_bounds__(BT)
@@ -311,6 +392,23 @@ extern "C" int ecb200_reverse_graph(const int32_t* idx, int B, int N, int k, int
   const long long M = (long long)B * N, E = M * k;
   ECB_REQUIRE(E < (1LL << 31), "ecb200_reverse_graph: B*N*k = %lld does not fit int32", E);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // destination ranges per cloud: about one CTA per SM, each range's counters in shared memory
+    int parts = ecb200::ceil_div(ecb200::kNumSMs, B);
+    if (parts > 8) parts = 8;   // every CTA re-reads the cloud's whole neighbour list
+    int span = ecb200::ceil_div(N, parts);
+    if ((size_t)span * 2 * sizeof(int) > 160 * 1024) span = 160 * 1024 / (2 * sizeof(int));
+    parts = ecb200::ceil_div(N, span);
+    if (B <= 65535 && parts <= 64) {
+      const size_t smem = (size_t)span * 2 * sizeof(int);
+      static thread_local bool seen[ecb200::kMaxDevices] = {};
+      if (ecb200::first_use_on_device(seen))
+        ECB_CUDA(cudaFuncSetAttribute(rev_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      rev_cloud_kernel<<<dim3(parts, B), 1024, smem, st>>>(idx, N, k, M, span, rowptr, src);
+      ECB_LAUNCH_CHECK("rev_cloud_kernel");
+      return ECB200_OK;
+    }
+  }
   ECB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)M, st));
   const unsigned eb = (unsigned)ecb200::ceil_div64(E, 256);
   rev_count_kernel<<<eb, 256, 0, st>>>(idx, N, k, E, cursor);
