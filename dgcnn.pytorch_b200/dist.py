@@ -57,33 +57,71 @@ def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class FlatGradSync:
-    """Data-parallel gradient averaging as ONE all-reduce of a flat fp32 buffer.
+    """Data-parallel gradient averaging over a flat fp32 buffer, overlapped with the backward.
 
     Every parameter's ``.grad`` is a view into ``self.flat``; autograd accumulates into the
-    views in place, so after ``backward()`` a single NCCL all-reduce (over NVLink / NVSwitch,
-    NVLS when available) on the compute stream averages all gradients -- no bucketing
-    threads, no hooks, and the call is capturable in a CUDA graph together with the step.
-    DGCNN-cls has 1.8 M parameters (7 MB): latency, not bandwidth, is what matters here.
+    views in place.  The parameters are laid out in two buckets: ``late`` (those whose
+    gradients are produced at the very end of the backward pass -- the EdgeConv layers, which
+    come first in the network) and ``early`` (conv5 and the head: 95 % of the bytes, complete
+    after the first few per cent of the backward).  As soon as the last ``early`` gradient has
+    been accumulated, its all-reduce is issued on a side stream and runs under the EdgeConv
+    backward; ``average()`` reduces the small ``late`` bucket and joins the side stream.
+    No bucketing threads; everything is capturable in a CUDA graph together with the step.
     Usage per step:  sync.zero() ; loss.backward() ; sync.average() ; optimizer.step()
     """
 
-    def __init__(self, params, group=None):
+    def __init__(self, params, group=None, late=None, overlap: bool = True):
+        """``late``: optional predicate(param_index, param) -> bool selecting the late bucket
+        (default: the first 12 parameters = conv1..conv4 + their BatchNorms of a DGCNN)."""
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if late is None:
+            late = lambda i, p: i < 12  # noqa: E731
+        late_ps = [p for i, p in enumerate(self.params) if late(i, p)]
+        early_ps = [p for i, p in enumerate(self.params) if not late(i, p)]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         o = 0
-        for p in self.params:
+        for p in late_ps + early_ps:
             p.grad = self.flat[o:o + p.numel()].view_as(p)
             o += p.numel()
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        n_late = sum(p.numel() for p in late_ps)
+        self.flat_late, self.flat_early = self.flat[:n_late], self.flat[n_late:]
+        self.overlap = bool(overlap and self.world > 1 and early_ps and dev.type == "cuda")
+        self._pending = len(early_ps)
+        self._left = self._pending
+        self._early_done = False
+        self._side = torch.cuda.Stream(device=dev) if self.overlap else None
+        if self.overlap:
+            for p in early_ps:
+                p.register_post_accumulate_grad_hook(self._on_early_grad)
+
+    def _on_early_grad(self, _param) -> None:
+        self._left -= 1
+        if self._left == 0:
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                dist.all_reduce(self.flat_early, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat_early.mul_(1.0 / self.world)
+            self._early_done = True
 
     def zero(self) -> None:
         self.flat.zero_()
+        self._left = self._pending
+        self._early_done = False
 
     def average(self) -> None:
-        if self.world > 1:
+        if self.world <= 1:
+            return
+        if self._early_done:
+            if self.flat_late.numel():
+                dist.all_reduce(self.flat_late, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat_late.mul_(1.0 / self.world)
+            torch.cuda.current_stream().wait_stream(self._side)
+        else:   # hooks did not fire (e.g. a parameter got no gradient): reduce everything here
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / self.world)
 
@@ -116,7 +154,7 @@ class PeerStatsExchange:
         self.handle = symm_mem.rendezvous(self.buf, self.group)
         self.bufs_dev = int(self.handle.buffer_ptrs_dev)     # device array of `world` base pointers
         self.seq = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.max_values = (nbytes - 2 * self.world * 8) // (2 * self.world * 8)
+        self.max_values = nbytes // (2 * self.world * 16)
         torch.cuda.synchronize()
         dist.barrier(self.group)                              # every buffer is zeroed before any push
 
