@@ -114,3 +114,36 @@ def test_syncbn_exchange_matches_single_process(tmp_path):
         assert torch.allclose(parts[0][key], parts[1][key], rtol=0, atol=0)
         assert torch.allclose(parts[0][key], grad, rtol=1e-7, atol=1e-9)
         assert torch.allclose(parts[0][key + "_local"] + parts[1][key + "_local"], grad, rtol=1e-7, atol=1e-9)
+
+
+def _grad_sync_worker(rank, world, port, out):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from dgcnn_pytorch_b200 import dist as ecd
+    torch.set_num_threads(1)
+    ecd.init_from_env("gloo")
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(3, 2)) for _ in range(15)]     # 12 "late" + 3 "early"
+    sync = ecd.FlatGradSync(params)
+    assert not sync.overlap                                  # CPU: no side stream, one flat all-reduce
+    assert sync.flat_late.numel() == 12 * 6 and sync.flat_early.numel() == 3 * 6
+    # every .grad is a view into the flat buffer, late bucket first
+    assert params[0].grad.data_ptr() == sync.flat.data_ptr()
+    assert params[12].grad.data_ptr() == sync.flat_early.data_ptr()
+    sync.zero()
+    loss = sum(((rank + 1.0) * (i + 1) * p).sum() for i, p in enumerate(params))
+    loss.backward()                                          # d/dp = (rank+1)*(i+1), accumulated in place
+    assert params[3].grad.data_ptr() == sync.flat.data_ptr() + 3 * 6 * 4
+    sync.average()
+    torch.save([p.grad.clone() for p in params], f"{out}.{rank}")
+    dist.destroy_process_group()
+
+
+def test_flat_grad_sync_buckets_and_average(tmp_path):
+    world, port, out = 2, _free_port(), str(tmp_path / "g")
+    mp.start_processes(_grad_sync_worker, args=(world, port, out), nprocs=world, join=True, start_method="spawn")
+    a, b = (torch.load(f"{out}.{r}") for r in range(world))
+    for i, (ga, gb) in enumerate(zip(a, b)):
+        assert torch.equal(ga, gb)
+        assert torch.allclose(ga, torch.full((3, 2), 1.5 * (i + 1)))      # mean of (1, 2) * (i+1)
