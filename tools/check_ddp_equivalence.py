@@ -26,8 +26,9 @@ args = SimpleNamespace(emb_dims=128, k=k, dropout=0.0)
 torch.manual_seed(3)
 ref = ec.DGCNN_cls(args).to(dev).train()                      # identical on every rank (same seed)
 sd = {n: v.clone() for n, v in ref.state_dict().items()}
-x = orc.synthetic_xyz(B, N, seed=5).to(dev)
-y = torch.randint(0, 40, (B,), generator=torch.Generator().manual_seed(5)).to(dev)
+off = int(os.environ.get("DDP_CHECK_OFFSET", "0"))     # clouds [off, off+B) of a larger batch
+x = orc.synthetic_xyz(B + off, N, seed=5)[off:].contiguous().to(dev)
+y = torch.randint(0, 40, (B + off,), generator=torch.Generator().manual_seed(5))[off:].to(dev)
 
 model = ec.DGCNN_cls(args).to(dev)
 model.load_state_dict(sd)
