@@ -61,6 +61,36 @@ def test_version_and_error_string(ec):
         ec._lib.call("ecb200_edge_gather", one, one, one, 1, 8, 2, 6, one, one, None, None, None)
 
 
+def test_argument_validation_of_the_newer_entry_points(ec):
+    """Every entry point checks its arguments before touching the device (no GPU needed)."""
+    one = ctypes.c_void_p(16)
+    call = ec._lib.call
+    with pytest.raises(RuntimeError, match="multiple of 32"):     # tensor-core kNN takes C = 32..128
+        call("ecb200_knn_tc", one, one, one, 1, 48, 64, 4, 1, one, one, 1 << 30, None)
+    with pytest.raises(RuntimeError, match="exceeds 40"):
+        call("ecb200_knn_tc", one, one, one, 1, 64, 256, 41, 1, one, one, 1 << 30, None)
+    with pytest.raises(RuntimeError, match="workspace too small"):
+        call("ecb200_knn_tc", one, one, one, 2, 64, 256, 20, 1, one, one, 16, None)
+    assert ec._lib.load().ecb200_knn_tc_workspace_bytes(2, 256, 20) == 2 * 2 * 256 * 56 * 8
+    with pytest.raises(RuntimeError, match="come in pairs"):
+        call("ecb200_prepare_weights", one, 8, 4, 0, one, one, None, None, None, None)
+    with pytest.raises(RuntimeError, match="C in \\{32,64,128\\}"):
+        call("ecb200_gemm_dx_tc", one, one, one, one, 1, 48, 64, 64, one, None)
+    with pytest.raises(RuntimeError, match="fused mode"):          # dU_in without the hi/lo outputs
+        call("ecb200_bwd_dense", one, one, one, one, one, one, 1, 1, 8, 8, None, one, None, None, None)
+    with pytest.raises(RuntimeError, match="fused mode"):
+        call("ecb200_bwd_scatter", one, one, one, one, one, one, one, one, 1, 8, 2, 8, None, one, None, None, None)
+    with pytest.raises(RuntimeError, match="ld_pm"):
+        call("ecb200_edge_apply", one, one, one, 0.2, 1, 8, 8, None, one, 4, None)
+    with pytest.raises(RuntimeError, match="bad shape"):
+        call("ecb200_embed_pool", one, one, one, 0.2, 1, 8, 6, one, one, None)   # E % 4 != 0
+    with pytest.raises(RuntimeError, match="outside"):
+        call("ecb200_peer_allreduce", one, 5000, one, 0, 2, one, None)
+    with pytest.raises(RuntimeError, match="bad rank/world"):
+        call("ecb200_peer_allreduce", one, 8, one, 2, 2, one, None)
+    assert ec._lib.load().ecb200_peer_buffer_bytes(8) == 2 * 8 * 4160 * 16
+
+
 def test_cpu_tensors_are_rejected_not_served(ec):
     x = torch.randn(2, 3, 16)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
