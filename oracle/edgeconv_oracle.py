@@ -14,6 +14,8 @@ reference file ``/root/reference/models/dgcnn.py``:
 * ``edgeconv_block_oracle``            <- ``conv{n}`` Sequential + max over k
                                           dgcnn.py:54-73 applied at :84-98
 * ``DGCNNOracle``                      <- ``class DGCNN``       dgcnn.py:47-103
+* ``embed_pool_oracle``                <- conv5's BatchNorm2d + LeakyReLU (dgcnn.py:75-78,
+                                          :102) + the cls head's max | avg pooling
 
 Parity pin: the reference ships no tests or golden vectors (SURVEY.md §4,
 §8c), so the pins are generated HERE by ``oracle/make_golden.py``, which
@@ -187,6 +189,21 @@ class DGCNNClsOracle(nn.Module):
         f = h.dp1(F.leaky_relu(h.bn6(h.linear1(f)), negative_slope=0.2))
         f = h.dp2(F.leaky_relu(h.bn7(h.linear2(f)), negative_slope=0.2))
         return h.linear3(f)
+
+
+def embed_pool_oracle(z: torch.Tensor, B: int, N: int, gamma: torch.Tensor, beta: torch.Tensor,
+                      running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
+                      training: bool, slope: float = 0.2, eps: float = 1e-5,
+                      momentum: float = 0.1) -> torch.Tensor:
+    """conv5's BatchNorm2d + LeakyReLU (dgcnn.py:75-78 applied at :102) on conv5's raw output
+    ``z`` [B*N, E] (point-major rows), followed by the pooling upstream DGCNN_cls applies to the
+    embedding (adaptive_max_pool1d | adaptive_avg_pool1d over the N points, as in
+    ``DGCNNClsOracle.forward``) -> [B, 2E].  Checker for the fused embed_pool kernels."""
+    E = z.shape[1]
+    zz = z.view(B, N, E).permute(0, 2, 1).unsqueeze(-1)                 # [B,E,N,1] as conv5 emits it
+    y = F.batch_norm(zz, running_mean, running_var, gamma, beta, training, momentum, eps)
+    y = F.leaky_relu(y, slope).squeeze(-1)                               # [B,E,N]
+    return torch.cat((F.adaptive_max_pool1d(y, 1).view(B, -1), F.adaptive_avg_pool1d(y, 1).view(B, -1)), 1)
 
 
 def smoothed_ce_oracle(pred: torch.Tensor, gold: torch.Tensor, eps: float = 0.2) -> torch.Tensor:

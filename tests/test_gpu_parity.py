@@ -409,16 +409,6 @@ def test_full_size_properties(ec):
 
 
 # ------------------------------------ conv5's BatchNorm + LeakyReLU fused with the cls pooling
-def _embed_pool_reference(z, B, N, gamma, beta, rm, rv, training, slope=0.2, eps=1e-5, momentum=0.1):
-    """dgcnn.py:75-78,:102 (BatchNorm2d + LeakyReLU of conv5's output) followed by upstream
-    DGCNN_cls's max | mean over the points, in plain torch on the dtype / device of z."""
-    E = z.shape[1]
-    zz = z.view(B, N, E).permute(0, 2, 1).unsqueeze(-1)                # [B,E,N,1]
-    y = torch.nn.functional.batch_norm(zz, rm, rv, gamma, beta, training, momentum, eps)
-    y = torch.nn.functional.leaky_relu(y, slope).squeeze(-1)           # [B,E,N]
-    return torch.cat((y.max(dim=-1)[0], y.mean(dim=-1)), dim=1)
-
-
 @pytest.mark.parametrize("B,N,E", [(4, 256, 64), (3, 77, 20), (2, 1024, 1024)])
 @pytest.mark.parametrize("training", [True, False])
 def test_embed_pool_vs_torch_fp64(ec, B, N, E, training):
@@ -432,7 +422,7 @@ def test_embed_pool_vs_torch_fp64(ec, B, N, E, training):
     # fp64 reference
     zr, gr, br = (t.double().clone().requires_grad_(True) for t in (z, gamma, beta))
     rmr, rvr = rm.double().clone(), rv.double().clone()
-    pr = _embed_pool_reference(zr, B, N, gr, br, rmr, rvr, training)
+    pr = orc.embed_pool_oracle(zr, B, N, gr, br, rmr, rvr, training)
     (pr * gout.double()).sum().backward()
     d = dev()
     zg, gg, bg = (t.to(d).requires_grad_(True) for t in (z, gamma, beta))

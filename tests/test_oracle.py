@@ -126,3 +126,25 @@ def test_split_weight_identity_fp64():
     sel = torch.where(gamma >= 0, e.max(dim=2)[0], e.min(dim=2)[0])
     out = torch.nn.functional.leaky_relu(a * sel + b, 0.2).transpose(1, 2)
     assert torch.allclose(out, ref, rtol=1e-10, atol=1e-12)
+
+
+def test_embed_pool_oracle_is_the_tail_of_the_cls_oracle():
+    """embed_pool_oracle(conv5's raw output) == what DGCNNClsOracle feeds its head (conv5's
+    BatchNorm + LeakyReLU, dgcnn.py:75-78,:102, then max | avg pooling over the points)."""
+    from types import SimpleNamespace
+    torch.manual_seed(0)
+    args = SimpleNamespace(emb_dim=24, k=5, dropout=0.0)
+    net = orc.DGCNNClsOracle(args).train()
+    x = orc.synthetic_xyz(3, 40, seed=2)
+    B, N = 3, 40
+    captured = {}
+    h1 = net.backbone.conv5[0].register_forward_hook(lambda m, i, o: captured.__setitem__("z", o.detach()))
+    h2 = net.head.linear1.register_forward_hook(lambda m, i, o: captured.__setitem__("pooled", i[0].detach()))
+    bn = net.backbone.conv5[1]
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    net(x)
+    h1.remove(); h2.remove()
+    z = captured["z"].squeeze(-1).permute(0, 2, 1).reshape(B * N, -1)      # [B,E,N,1] -> [B*N,E]
+    pooled = orc.embed_pool_oracle(z, B, N, bn.weight.detach(), bn.bias.detach(), rm0, rv0, True)
+    assert torch.allclose(pooled, captured["pooled"], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(rm0, bn.running_mean) and torch.allclose(rv0, bn.running_var)
