@@ -14,6 +14,8 @@ reference file ``/root/reference/models/dgcnn.py``:
 * ``edgeconv_block_oracle``            <- ``conv{n}`` Sequential + max over k
                                           dgcnn.py:54-73 applied at :84-98
 * ``DGCNNOracle``                      <- ``class DGCNN``       dgcnn.py:47-103
+* ``two_conv_edge_block_oracle``       <- ``PositionEmbedding`` conv1 -> conv2 -> max
+                                          models/layers.py:45-52 (row f-1, next round)
 * ``embed_pool_oracle``                <- conv5's BatchNorm2d + LeakyReLU (dgcnn.py:75-78,
                                           :102) + the cls head's max | avg pooling
 
@@ -189,6 +191,21 @@ class DGCNNClsOracle(nn.Module):
         f = h.dp1(F.leaky_relu(h.bn6(h.linear1(f)), negative_slope=0.2))
         f = h.dp2(F.leaky_relu(h.bn7(h.linear2(f)), negative_slope=0.2))
         return h.linear3(f)
+
+
+def two_conv_edge_block_oracle(x: torch.Tensor, k: int, block1: nn.Sequential, block2: nn.Sequential,
+                               idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The two-conv edge block of the reference's ``PositionEmbedding`` (models/layers.py:45-52;
+    also the shape of upstream part-seg / sem-seg EdgeConv blocks), SURVEY.md §8 row f-1:
+        get_graph_feature(x, k) -> conv1 (Conv2d 1x1 + BN2d + LeakyReLU) -> conv2 (same) -> max over k
+    x [B,C,N] -> [B,Co2,N].  ``block1`` / ``block2`` are the reference's own Sequentials.  The first
+    conv splits as W.[x_j ; x_i] = U_j + V_i like every EdgeConv layer; the second is a genuine
+    per-edge GEMM on a tensor a fused kernel would never materialise.  Not built on the GPU in
+    round 1: this restatement and its fixture pin the row for the next round."""
+    gf = graph_feature_oracle(x, k=k, idx=idx)          # [B,2C,N,k]   layers.py:45
+    t = block1(gf)                                      # layers.py:48
+    t = block2(t)                                       # layers.py:50
+    return t.max(dim=-1, keepdim=False)[0]              # layers.py:52
 
 
 def embed_pool_oracle(z: torch.Tensor, B: int, N: int, gamma: torch.Tensor, beta: torch.Tensor,

@@ -169,6 +169,49 @@ def case_dgcnn(ref):
         **{f"idx_eval{n}": t for n, t in enumerate(idx_eval)})
 
 
+def case_two_conv_block():
+    """Row f-1: the two-conv edge block of the reference's PositionEmbedding
+    (models/layers.py:45-52), captured from the unmodified module by a forward hook on its
+    third conv (whose input is the block's output after the max over k)."""
+    sys.path.insert(0, REF)
+    from models.layers import PositionEmbedding  # unmodified reference module
+    sys.path.pop(0)
+    torch.manual_seed(31)
+    pe = PositionEmbedding(SimpleNamespace(k=6)).train()
+    with torch.no_grad():
+        for bn in (pe.bn1, pe.bn2):
+            bn.weight.normal_(1.0, 0.4)
+            bn.weight[::4] *= -1.0
+            bn.bias.normal_(0.0, 0.2)
+    sd = {k_: v.clone() for k_, v in pe.state_dict().items() if k_.startswith(("conv1.", "conv2."))}
+    x = orc.synthetic_xyz(2, 64, seed=31)
+    got = {}
+    h = pe.conv3.register_forward_hook(lambda m, i, o: got.__setitem__("t", i[0]))
+    xr = x.clone().requires_grad_(True)
+    pe(xr)
+    h.remove()
+    t = got["t"]                                          # [B,128,N]
+    gout = torch.randn(t.shape, generator=torch.Generator().manual_seed(32))
+    (t * gout).sum().backward()
+    # the oracle, on fresh modules carrying the same parameters and the initial running statistics
+    b1 = torch.nn.Sequential(torch.nn.Conv2d(6, 64, 1, bias=False), torch.nn.BatchNorm2d(64), torch.nn.LeakyReLU(0.2))
+    b2 = torch.nn.Sequential(torch.nn.Conv2d(64, 128, 1, bias=False), torch.nn.BatchNorm2d(128), torch.nn.LeakyReLU(0.2))
+    b1.load_state_dict({k_[len("conv1."):]: v for k_, v in sd.items() if k_.startswith("conv1.")})
+    b2.load_state_dict({k_[len("conv2."):]: v for k_, v in sd.items() if k_.startswith("conv2.")})
+    b1.train(); b2.train()
+    xo = x.clone().requires_grad_(True)
+    to = orc.two_conv_edge_block_oracle(xo, 6, b1, b2)
+    (to * gout).sum().backward()
+    assert torch.equal(t, to)
+    assert torch.equal(xr.grad, xo.grad)
+    assert torch.equal(pe.conv1[0].weight.grad, b1[0].weight.grad) and torch.equal(pe.conv2[0].weight.grad, b2[0].weight.grad)
+    assert torch.equal(pe.bn2.running_var, b2[1].running_var)
+    npz("two_conv_block_B2_N64_k6.npz", x=x, k=6, gout=gout, out=t, dx=xr.grad,
+        dw1=pe.conv1[0].weight.grad, dw2=pe.conv2[0].weight.grad,
+        dgamma2=pe.bn2.weight.grad, dbeta2=pe.bn2.bias.grad,
+        **{f"sd.{k_}": v for k_, v in sd.items()})
+
+
 def main():
     torch.set_num_threads(1)        # deterministic reduction order
     os.makedirs(GOLD, exist_ok=True)
@@ -177,6 +220,7 @@ def main():
     case_graph_feature(ref)
     case_block(ref)
     case_dgcnn(ref)
+    case_two_conv_block()
     print("oracle == reference on every case; fixtures written")
 
 

@@ -148,3 +148,21 @@ def test_embed_pool_oracle_is_the_tail_of_the_cls_oracle():
     pooled = orc.embed_pool_oracle(z, B, N, bn.weight.detach(), bn.bias.detach(), rm0, rv0, True)
     assert torch.allclose(pooled, captured["pooled"], rtol=1e-6, atol=1e-6)
     assert torch.allclose(rm0, bn.running_mean) and torch.allclose(rv0, bn.running_var)
+
+
+def test_two_conv_edge_block_matches_reference():
+    """Row f-1 (next round): the reference PositionEmbedding's conv1 -> conv2 -> max over k
+    (models/layers.py:45-52), recorded from the unmodified module."""
+    g = load_golden("two_conv_block_B2_N64_k6.npz")
+    b1 = torch.nn.Sequential(torch.nn.Conv2d(6, 64, 1, bias=False), torch.nn.BatchNorm2d(64), torch.nn.LeakyReLU(0.2))
+    b2 = torch.nn.Sequential(torch.nn.Conv2d(64, 128, 1, bias=False), torch.nn.BatchNorm2d(128), torch.nn.LeakyReLU(0.2))
+    b1.load_state_dict({k[len("sd.conv1."):]: v for k, v in g.items() if k.startswith("sd.conv1.")})
+    b2.load_state_dict({k[len("sd.conv2."):]: v for k, v in g.items() if k.startswith("sd.conv2.")})
+    b1.train(); b2.train()
+    x = g["x"].clone().requires_grad_(True)
+    t = orc.two_conv_edge_block_oracle(x, g["k"], b1, b2)
+    (t * g["gout"]).sum().backward()
+    assert torch.equal(t, g["out"])
+    assert torch.equal(x.grad, g["dx"])
+    assert torch.equal(b1[0].weight.grad, g["dw1"]) and torch.equal(b2[0].weight.grad, g["dw2"])
+    assert torch.equal(b2[1].weight.grad, g["dgamma2"]) and torch.equal(b2[1].bias.grad, g["dbeta2"])
