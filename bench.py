@@ -14,8 +14,15 @@ label-smoothed CE, backward, SGD update.  Prints ONE JSON line (rank 0).
   roofline  the dominant kernel of the EdgeConv path against the measured HBM peak
   cpu_baseline  the oracle (CPU restatement of the reference) on the host cores, bounded sample
 
---impl reference times the reference's CPU implementation of the same step (the oracle port:
-the reference itself is Python under /root/reference and cannot travel to the GPU box).
+  roofline  the dominant kernel of the step (tensor-core kNN) against the 3xTF32 tensor roofline;
+            roofline_gather / roofline_edgeconv: the gather kernel against HBM and L2, and the whole
+            EdgeConv forward against its combined bound
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, a verbatim copy made by
+            baseline/install_ref.py) on the host cores, bounded sample
+  gpu_eager_reference  the same unmodified reference run eagerly on this B200, TF32 off
+
+--impl reference times the reference's own CPU implementation of the same step at the same batch
+(baseline/_ref; falls back to the oracle port only if that copy is missing).
 """
 from __future__ import annotations
 
@@ -31,7 +38,7 @@ import time
 from types import SimpleNamespace
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "oracle")):
+for p in (ROOT, os.path.join(ROOT, "baseline")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -39,6 +46,8 @@ import torch  # noqa: E402
 
 METRIC = "DGCNN-cls fwd+bwd clouds/sec (N=1024,k=20)"
 UNIT = "clouds/s"
+CONV5_NOTE = ("conv5 GEMM in cuDNN (library default TF32) on the channels-last concat; its BatchNorm + "
+              "LeakyReLU + max|avg pooling in own kernels (embed_pool); 3 head linears in torch")
 
 
 def parse():
@@ -55,6 +64,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
     ap.add_argument("--cpu-clouds", type=int, default=8, help="clouds per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-reference", action="store_true")
+    ap.add_argument("--no-kernel-profile", action="store_true")
     return ap.parse_args()
 
 
@@ -76,57 +87,120 @@ def workload_name(a):
 
 
 # ------------------------------------------------------------------- CPU reference arm
-def cpu_step_fn(a, clouds):
-    import edgeconv_oracle as orc
-    torch.manual_seed(1)
+def reference_model(a):
+    """(model, loss_fn, kind): the unmodified reference (baseline/_ref) + upstream cls head, or --
+    only when that copy is missing -- the oracle port of the same network."""
+    import ref_cls
     args = SimpleNamespace(emb_dim=a.emb, k=a.k, dropout=0.5)
-    model = orc.DGCNNClsOracle(args).train()
+    torch.manual_seed(1)
+    if ref_cls.available():
+        return ref_cls.RefDGCNNCls(args), ref_cls.reference_loss, "reference"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import edgeconv_oracle as orc            # the one other place bench.py may execute oracle/
+    return orc.DGCNNClsOracle(args), orc.smoothed_ce_oracle, "port"
+
+
+def time_cpu(a, clouds, steps, warmup, budget_s=None):
+    """Reference train step on the host cores: (clouds/s, s/step, cores, kind, steps timed)."""
+    from dgcnn_pytorch_b200.synthetic import synthetic_xyz
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    model, loss_fn, kind = reference_model(a)
+    model.train()
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
-    x = orc.synthetic_xyz(clouds, a.points, seed=1)
+    x = synthetic_xyz(clouds, a.points, seed=1)
     y = torch.randint(0, 40, (clouds,), generator=torch.Generator().manual_seed(1))
 
     def step():
         opt.zero_grad(set_to_none=True)
-        loss = orc.smoothed_ce_oracle(model(x), y)
+        loss = loss_fn(model(x), y)
         loss.backward()
         opt.step()
         return loss.item()
-    return step
-
-
-def time_cpu(a, clouds, steps, warmup):
-    cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
-    step = cpu_step_fn(a, clouds)
     for _ in range(warmup):
         step()
     ts = []
+    t_begin = time.perf_counter()
     for _ in range(steps):
         t0 = time.perf_counter()
         step()
         ts.append(time.perf_counter() - t0)
-    return clouds / statistics.median(ts), statistics.median(ts), cores
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s:
+            break
+    sec = sum(ts) / len(ts)
+    return clouds / sec, sec, cores, kind, len(ts)
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    clouds = a.cpu_clouds
-    cps, sec, cores = time_cpu(a, clouds, max(1, a.steps), max(1, a.warmup))
+    # the same configuration as the b200 arm: B clouds per step, same N, k, emb, same train step.
+    # One step is seconds of CPU work, so warm-up is capped at 1 and the timed loop stops early
+    # if it would exceed ~4 minutes (the number of steps actually timed is reported).
+    clouds = a.batch
+    cps, sec, cores, kind, done = time_cpu(a, clouds, max(1, a.steps), min(max(1, a.warmup), 1), budget_s=240.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": cps, "unit": UNIT, "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3 * a.batch / clouds,
+        "steps": done, "warmup": min(max(1, a.warmup), 1), "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(a), "device": "host CPU"},
-        "cpu_baseline": {"value": cps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{clouds} clouds per step (same N, k, emb, same step), median of "
-                                   f"{max(1, a.steps)} steps, torch CPU threads = {cores}"},
+        "config": {"workload": workload_name(a), "device": "host CPU", "same_config": True,
+                   "global_batch": clouds,
+                   "code": "unmodified reference models/dgcnn.py (baseline/_ref) + upstream cls head"
+                           if kind == "reference" else "oracle port (baseline/_ref missing)"},
+        "cpu_baseline": {"value": cps, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{clouds} clouds per step (the full batch, same N, k, emb, same train step), "
+                                   f"mean of {done} steps, torch CPU threads = {cores}"},
         "e2e": {"value": cps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def time_gpu_eager_reference(a, dev, B):
+    """The unmodified reference (same network, same train step) run eagerly on this GPU with TF32
+    off: the strongest existing implementation of the path."""
+    import ref_cls
+    from dgcnn_pytorch_b200.synthetic import synthetic_xyz
+    if not ref_cls.available():
+        return {"unavailable": "baseline/_ref missing"}
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(1)
+        model = ref_cls.RefDGCNNCls(SimpleNamespace(emb_dim=a.emb, k=a.k, dropout=0.5)).to(dev).train()
+        opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+        x = synthetic_xyz(B, a.points, seed=1).to(dev)
+        y = torch.randint(0, 40, (B,), generator=torch.Generator().manual_seed(1)).to(dev)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = ref_cls.reference_loss(model(x), y)
+            loss.backward()
+            opt.step()
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        n = 20
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            step()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / n
+        peak = torch.cuda.max_memory_allocated(dev)
+        del model, opt, x, y
+        torch.cuda.empty_cache()
+        return {"value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": n, "warmup": 5,
+                "tf32": False, "peak_mem_bytes": int(peak),
+                "what": "unmodified reference DGCNN (baseline/_ref) + cls head, eager torch on this GPU, same step"}
+    except Exception as exc:  # noqa: BLE001 - a comparator leg never takes the line down
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
 
 
 # ---------------------------------------------------------------------------- clocks
@@ -217,14 +291,67 @@ def edge_layer_shapes(a):
     return [(3, 64), (64, 64), (64, 128), (128, 256)]
 
 
-def gather_bytes(M, k, Co, training=True):
-    """Algorithmic bytes of one ecb200_edge_gather launch: idx + the k gathered
-    U rows + the V row in; sel, arg (+ esum in training) out.  SpMM convention: every gathered
-    row counts once wherever it is served from."""
+def q_edge_bytes(M, C, k, Co):
+    """algorithmic bytes of the edge-MLP + max of one layer, SpMM convention (every
+    gathered row counts once, wherever it is served from): x in + idx in + k gathered U rows + out."""
+    return 4 * M * (C + k + k * Co + Co)
+
+
+def gather_kernel_bytes(M, k, Co, training=True):
+    """What ecb200_edge_gather itself moves per launch: idx + the k gathered U rows + the V row in;
+    sel, arg (+ esum in training) out.  Reported beside the SURVEY figure."""
     b = 4 * M * k + 4 * M * k * Co + 4 * M * Co + 4 * M * Co + M * Co
     if training:
         b += 4 * M * Co
     return b
+
+
+# forward kernels of the EdgeConv path (kNN + edge MLP + max), by name fragments of the kernels
+EDGE_FWD_KERNELS = ("knn_tc_kernel", "knn_xyz_kernel", "knn_fma_kernel", "sqnorms_kernel", "split_tf32_kernel",
+                    "prepare_weights_kernel", "pack_weight_kernel", "gemm_tile_kernel", "edge_gather_kernel",
+                    "bn_finalize_kernel", "edge_apply_kernel", "bn_update_running_kernel")
+
+
+def short_kernel_name(name):
+    """'void <unnamed>::knn_tc_kernel<32, 0>(const float*, ...)' -> 'knn_tc_kernel<32, 0>'"""
+    n = name
+    if n.startswith("void "):
+        n = n[5:]
+    depth, out = 0, []
+    for ch in n:                      # cut the argument list (first '(' at template depth 0)
+        if ch == "<":
+            depth += 1
+        elif ch == ">":
+            depth -= 1
+        elif ch == "(" and depth == 0:
+            break
+        out.append(ch)
+    n = "".join(out).replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+    return n[:96]
+
+
+def profile_graph_kernels(replay, nsteps):
+    """Per-kernel device time INSIDE the replayed CUDA graph (CUPTI activity records through
+    torch.profiler): {kernel: {"calls_per_step", "us_per_step"}}.  Not the timed region -- the
+    headline comes from CUDA events without any profiler -- but the same graph, same inputs."""
+    from torch.profiler import ProfilerActivity, profile
+    replay(0)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(nsteps):
+            replay(i)
+        torch.cuda.synchronize()
+    agg = {}
+    for ev in prof.events():
+        if str(getattr(ev, "device_type", "")).endswith("CUDA") and ev.name and not ev.name.startswith("Memcpy") \
+                and not ev.name.startswith("Memset"):
+            dur = getattr(ev, "device_time", None)
+            if dur is None:
+                dur = getattr(ev, "cuda_time", 0.0)
+            d = agg.setdefault(short_kernel_name(ev.name), [0, 0.0])
+            d[0] += 1
+            d[1] += float(dur)
+    return {n: {"calls_per_step": c / nsteps, "us_per_step": us / nsteps} for n, (c, us) in agg.items()}
 
 
 # ------------------------------------------------------------------------ B200 arm
@@ -232,6 +359,7 @@ def run_b200(a):
     import torch.distributed as dist
 
     import dgcnn_pytorch_b200 as ec
+    from dgcnn_pytorch_b200.synthetic import synthetic_xyz
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -248,7 +376,6 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")   # collectives get graph-captured
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     B = a.batch if a.scaling == "weak" else max(1, a.batch // world)
     N, k = a.points, a.k
@@ -260,26 +387,23 @@ def run_b200(a):
     stats_exchange = None
     if world > 1:
         # SyncBatchNorm semantics for every BN (the EdgeConv ones exchange their statistics
-        # inside the fused op); gradients averaged by one flat all-reduce per step
-        from dgcnn_pytorch_b200.dist import FlatGradSync
+        # inside the fused op, the head's through the same exchange); gradients averaged by one
+        # flat all-reduce per step
+        from dgcnn_pytorch_b200.dist import FlatGradSync, PeerStatsExchange
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
         for p in model.parameters():          # identical replicas
             dist.broadcast(p.data, 0)
         sync = FlatGradSync(model.parameters())
         if os.environ.get("ECB200_STATS_EXCHANGE", "peer") == "peer":
-            try:   # BatchNorm statistics over NVLink peer memory, one kernel per exchange
-                from dgcnn_pytorch_b200.dist import PeerStatsExchange
-                peer_exchange = PeerStatsExchange.enable()
-                stats_exchange = "one-kernel push exchange over NVLink peer memory (symmetric memory)"
-            except Exception as exc:  # noqa: BLE001 - transport fallback, reported in the JSON line
-                stats_exchange = f"NCCL all-reduce (peer memory unavailable: {type(exc).__name__}: {exc})"[:160]
+            # BatchNorm statistics over NVLink peer memory, one kernel per exchange; every rank
+            # must agree on the transport, or the pushing ranks would wait for words that never come
+            stats_exchange = PeerStatsExchange.enable_collectively()
         else:
             stats_exchange = "NCCL all-reduce"
     opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
 
-    import edgeconv_oracle as orc   # only for the synthetic-input generator and the cpu_baseline leg
     npool = 4
-    host_x = [orc.synthetic_xyz(B, N, seed=100 * rank + i).pin_memory() for i in range(npool)]
+    host_x = [synthetic_xyz(B, N, seed=100 * rank + i).pin_memory() for i in range(npool)]
     host_y = [torch.randint(0, 40, (B,), generator=torch.Generator().manual_seed(7 * rank + i)).pin_memory()
               for i in range(npool)]
     dev_x = [t.to(dev) for t in host_x]
@@ -327,7 +451,7 @@ def run_b200(a):
     t_clock0 = time.perf_counter()
 
     # ---- timed region A: eager launches, per-step CUDA events, L2 flushed between steps,
-    #      every C-ABI entry bracketed by events (per-kernel durations for the roofline)
+    #      every C-ABI entry bracketed by events (fallback per-kernel durations)
     def timed(fn, count):
         evs = []
         barrier()
@@ -390,6 +514,17 @@ def run_b200(a):
     t_clock1 = time.perf_counter()
     clocks = sampler.stop(t_clock0, t_clock1) if rank == 0 else None
 
+    # ---- per-kernel time inside the replayed graph (after the timed regions; single-rank runs)
+    kprof, kprof_err = None, None
+    if world == 1 and use_graph and not a.no_kernel_profile:
+        try:
+            def replay(i):
+                flush.zero_()
+                gstep(dev_x[i % npool], dev_y[i % npool])
+            kprof = profile_graph_kernels(replay, min(a.steps, 10))
+        except Exception as exc:  # noqa: BLE001
+            kprof_err = f"{type(exc).__name__}: {exc}"[:200]
+
     if rank != 0:
         finish(world)
         return
@@ -397,50 +532,110 @@ def run_b200(a):
     pk = peaks()
     clouds = B * world
     M = B * N
-    # roofline of the dominant EdgeConv kernel: the neighbour gather (HBM-bound by the SpMM
-    # convention).  Its launches differ per layer, so achieved = sum(bytes) / sum(time).
-    gather = entries.get("ecb200_edge_gather")
+    tf32x3_peak = pk["bf16_tflops"] / 2.0 / 3.0
+    layers = edge_layer_shapes(a)
+
+    def kernel_us(fragment):
+        """us per step of the kernels whose name contains `fragment`: in-graph profile if there is
+        one, else the eager event brackets of the matching entry point."""
+        if kprof:
+            return sum(v["us_per_step"] for n, v in kprof.items() if fragment in n)
+        return None
+
+    def entry_ms(name):
+        e = entries.get(name)
+        return e["total_ms"] / a.steps if e else None
+
+    # roofline 1 (dominant kernel of the step): tensor-core kNN of the feature-space layers against
+    # the 3xTF32 tensor roofline (bf16 peak / 2 for TF32 / 3 MMAs per product); FLOPs = 2*M*N*C per
+    # layer (SURVEY 8d: norm terms and the error-compensation MMAs do not count)
     roof = None
-    if gather:
-        per_step_calls = gather["calls"] // a.steps
-        by = sum(gather_bytes(M, k, co) for _, co in edge_layer_shapes(a))
-        t_ms = gather["total_ms"] / a.steps
-        ach = by / (t_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_gather_traffic.json")
+    knn_flops = sum(2.0 * M * N * c for c, _ in layers if c % 32 == 0 and 32 <= c <= 128)
+    t_us = kernel_us("knn_tc_kernel<32, 0>") or kernel_us("knn_tc_kernel<32, false>")
+    src = "in-graph (CUPTI)"
+    if not t_us and entry_ms("ecb200_knn_tc"):
+        t_us, src = entry_ms("ecb200_knn_tc") * 1e3, "eager CUDA-event brackets"
+    if t_us:
+        ach = knn_flops / (t_us * 1e-6) / 1e12
+        roof = {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": ach, "peak": tf32x3_peak,
+                "unit": "TFLOP/s", "frac": ach / tf32x3_peak, "traffic": None,
+                "peak_source": pk["source"] + " bf16 burst / 2 (tf32) / 3 (3xTF32)",
+                "launches_per_step": 3, "flops_per_step": knn_flops, "us_per_step": t_us, "timing": src}
+    # roofline 2: the neighbour gather against HBM (SURVEY's Q_edge and the kernel's own byte count)
+    roof_gather = None
+    t_us = kernel_us("edge_gather_kernel")
+    src = "in-graph (CUPTI)"
+    if not t_us and entry_ms("ecb200_edge_gather"):
+        t_us, src = entry_ms("ecb200_edge_gather") * 1e3, "eager CUDA-event brackets"
+    if t_us:
+        q_survey = sum(q_edge_bytes(M, c, k, co) for c, co in layers)
+        q_kernel = sum(gather_kernel_bytes(M, k, co) for _, co in layers)
+        ach = q_survey / (t_us * 1e-6) / 1e9
+        traffic = lts = None
+        tpath = os.path.join(ROOT, "profiles", "r2_gather_traffic.json")
         if (a.batch, a.points, a.k) == (32, 1024, 20) and os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f)["dram_bytes_per_step"]     # ncu --set full capture, per step
-        roof = {"bound": "hbm", "kernel": "edge_gather_kernel", "achieved": ach, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic,
-                "peak_source": pk["source"], "launches_per_step": per_step_calls,
-                "algorithmic_bytes_per_step": by, "ms_per_step": t_ms}
-    # second roofline: the tensor-core kNN of the feature-space layers against the 3xTF32 tensor
-    # roofline (bf16 peak / 2 for TF32 / 3 MMAs per product); FLOPs = 2*M*N*C per layer
-    roof_knn = None
-    try:
-        ktc = entries.get("ecb200_knn_tc")
-        if ktc:
-            flops = sum(2.0 * M * N * c for c, _ in edge_layer_shapes(a) if c % 32 == 0 and 32 <= c <= 128)
-            t_ms = ktc["total_ms"] / a.steps
-            peak = pk["bf16_tflops"] / 2.0 / 3.0
-            ach = flops / (t_ms * 1e-3) / 1e12
-            roof_knn = {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": ach, "peak": peak,
-                        "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                        "peak_source": pk["source"] + " bf16 / 2 (tf32) / 3 (3xTF32)",
-                        "launches_per_step": ktc["calls"] // a.steps, "flops_per_step": flops,
-                        "ms_per_step": t_ms}
-    except Exception:  # noqa: BLE001 - an extra, never at the expense of the line
-        roof_knn = None
-    breakdown = {n: round(v["total_ms"] / a.steps, 4) for n, v in
-                 sorted(entries.items(), key=lambda kv: -kv[1]["total_ms"])}
+                tj = json.load(f)
+            traffic, lts = tj.get("dram_bytes_per_step"), tj.get("lts_bytes_per_step")
+        roof_gather = {"bound": "hbm", "kernel": "edge_gather_kernel", "achieved": ach, "peak": pk["hbm_gbs"],
+                       "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": traffic,
+                       "lts_bytes_per_step": lts,
+                       "note": "rows are served from L2 (DRAM traffic << algorithmic bytes): the binding resource is "
+                               "L2 bandwidth, the HBM fraction only says the SpMM-convention bytes move faster than HBM could",
+                       "algorithmic_bytes_per_step": q_survey, "kernel_bytes_per_step": q_kernel,
+                       "achieved_kernel_bytes_gbs": q_kernel / (t_us * 1e-6) / 1e9,
+                       "l2_gbs": (lts / (t_us * 1e-6) / 1e9) if lts else None,
+                       "us_per_step": t_us, "timing": src}
+    # roofline 3: xyz kNN against the FP32 FMA issue peak (3 FMAs per pair, one sweep is algorithmic)
+    roof_xyz = None
+    t_us = kernel_us("knn_xyz_kernel")
+    if not t_us and entry_ms("ecb200_knn"):
+        t_us = entry_ms("ecb200_knn") * 1e3
+    sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    fma_peak = 148 * 128 * sm_mhz * 1e6          # FMA/s
+    if t_us:
+        pairs = float(M) * N
+        roof_xyz = {"bound": "fp32-fma issue", "kernel": "knn_xyz_kernel", "pairs_per_s": pairs / (t_us * 1e-6),
+                    "fma_per_pair_algorithmic": 3, "frac_of_fma_peak": 3 * pairs / (t_us * 1e-6) / fma_peak,
+                    "fma_peak_per_s": fma_peak, "us_per_step": t_us}
+    # roofline 4: the whole fused EdgeConv forward (kNN + edge MLP + max, 4 layers) against its
+    # combined bound: Q_edge / HBM + F_knn / (TF32/3) + xyz pairs * 3 FMA / FMA peak
+    roof_edge = None
+    if kprof:
+        t_fwd = sum(v["us_per_step"] for n, v in kprof.items()
+                    if any(f in n for f in EDGE_FWD_KERNELS) and "EpiD" not in n)
+        q_survey = sum(q_edge_bytes(M, c, k, co) for c, co in layers)
+        bound_us = (q_survey / (pk["hbm_gbs"] * 1e9) + knn_flops / (tf32x3_peak * 1e12)
+                    + 3.0 * M * N / fma_peak) * 1e6
+        roof_edge = {"bound_us": bound_us, "measured_us": t_fwd, "frac": bound_us / t_fwd if t_fwd else None,
+                     "kernels": [f for f in EDGE_FWD_KERNELS],
+                     "what": "sum of the forward EdgeConv kernels inside the replayed graph (4 layers) vs "
+                             "SURVEY 8d: Q_edge/HBM + F_knn/(TF32/3) + xyz FMA bound"}
+    if kprof:
+        breakdown = {n: round(v["us_per_step"] / 1e3, 4) for n, v in
+                     sorted(kprof.items(), key=lambda kv: -kv[1]["us_per_step"])[:40]}
+        breakdown_src = "CUPTI kernel records of the replayed CUDA graph (separate pass after the timed region)"
+        breakdown_sum = sum(v["us_per_step"] for v in kprof.values()) / 1e3
+    else:
+        breakdown = {n: round(v["total_ms"] / a.steps, 4) for n, v in
+                     sorted(entries.items(), key=lambda kv: -kv[1]["total_ms"])}
+        breakdown_src = "CUDA-event brackets around the C-ABI calls of the eager pass" + (f" ({kprof_err})" if kprof_err else "")
+        breakdown_sum = sum(breakdown.values())
 
     cpu = None
-    if not a.no_cpu_baseline and world >= 1:
-        cps, sec, cores = time_cpu(a, a.cpu_clouds, 3, 1)
-        cpu = {"value": cps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{a.cpu_clouds} clouds per step of the same workload, 1 warm-up + median of 3 "
-                         f"steps ({sec:.2f} s/step)"}
+    if not a.no_cpu_baseline and world == 1:
+        try:
+            cps, sec, cores, kind, done = time_cpu(a, a.cpu_clouds, 3, 1, budget_s=60.0)
+            cpu = {"value": cps, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": f"{a.cpu_clouds} clouds per step of the same workload (the --impl reference arm runs "
+                             f"the full batch), 1 warm-up + mean of {done} steps ({sec:.2f} s/step)"}
+        except Exception as exc:  # noqa: BLE001
+            cpu = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    eager_ref = None
+    if world == 1 and not a.no_gpu_eager_reference:
+        del flush
+        torch.cuda.empty_cache()
+        eager_ref = time_gpu_eager_reference(a, dev, B)
 
     h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
     line = {
@@ -452,7 +647,7 @@ def run_b200(a):
                    "l2": "256 MiB buffer rewritten between timed steps (L2 flush)",
                    "cuda_graph": use_graph,
                    "eager_ms_per_step": eager_ms, "graph_ms_per_step": graph_ms,
-                   "graph_error": graph_err, "conv5_and_head": "conv5 GEMM in cuDNN (library default TF32) on the channels-last concat; its BatchNorm + LeakyReLU + max|avg pooling in own kernels (embed_pool); 3 head linears in torch",
+                   "graph_error": graph_err, "conv5_and_head": CONV5_NOTE,
                    "grad_sync": "one flat NCCL all-reduce per step" if world > 1 else None,
                    "bn_stats_exchange": stats_exchange},
         "clocks": clocks,
@@ -461,9 +656,14 @@ def run_b200(a):
         "gpu_launches": int(round(launches_per_step * a.steps)),
         "gpu_launches_per_step": launches_per_step,
         "roofline": roof,
-        "roofline_knn": roof_knn,
+        "roofline_gather": roof_gather,
+        "roofline_knn_xyz": roof_xyz,
+        "roofline_edgeconv": roof_edge,
         "kernel_ms_per_step": breakdown,
+        "kernel_ms_per_step_source": breakdown_src,
+        "kernel_ms_per_step_sum": breakdown_sum,
         "cpu_baseline": cpu,
+        "gpu_eager_reference": eager_ref,
     }
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

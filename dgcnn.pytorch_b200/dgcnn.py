@@ -50,7 +50,7 @@ def get_graph_feature(x: torch.Tensor, k: int = 20, knn_only: bool = False,
         src = x[:, 6:] if dim9 else x
         idx32 = ops.knn_op(src.contiguous(), int(k))
     else:
-        idx32 = idx.to(torch.int32)
+        idx32 = ops.check_neighbour_indices(idx, x.shape[0], x.shape[2])
     if knn_only:
         mode = ops.GF_KNN_ONLY
     elif disp_only:
@@ -92,6 +92,8 @@ def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
         raise RuntimeError("edgeconv_block expects a bias-free 1x1 Conv2d")
     x = _as_f32(x)
     B, C, N = x.shape
+    if idx is not None:
+        idx = ops.check_neighbour_indices(idx, B, N)
     xhi = xlo = None
     if ops.knn_uses_tensor_cores(C, N, int(k)) or (idx is not None and ops.point_gemm_uses_tensor_cores(C)):
         # feature-space layer: one split into tf32 hi/lo operands feeds both the tensor-core

@@ -132,9 +132,11 @@ class PeerStatsExchange:
     The exchange is a few hundred fp64 values per BatchNorm layer, ten times per step: pure
     latency.  Instead of an NCCL collective every rank pushes its vector straight into a slot
     of every peer's buffer (plain stores over NVLink into memory mapped with
-    torch.distributed._symmetric_memory), raises a flag, waits for the peers' flags and sums
-    the vectors in rank order (csrc/peer_exchange.cu).  No host involvement, capturable in a
-    CUDA graph, bit-identical results on every rank.
+    torch.distributed._symmetric_memory) as 8-byte {32 data bits | 32-bit sequence number} words
+    -- no flag, no fence: an aligned 8-byte store arrives atomically, so a word that carries the
+    expected sequence number also carries its data -- and sums the vectors that arrive in its own
+    buffer in rank order (csrc/peer_exchange.cu).  No host involvement, capturable in a CUDA
+    graph, bit-identical results on every rank.
 
         ex = PeerStatsExchange.enable()        # after init_process_group, once per process
     """
@@ -166,6 +168,28 @@ class PeerStatsExchange:
         ex = cls(group)
         ops.set_peer_exchange(ops.register_group(ex.group), ex)
         return ex
+
+    @classmethod
+    def enable_collectively(cls, group=None) -> str:
+        """``enable()`` on every rank of ``group``, then agree on the outcome: unless the symmetric-
+        memory setup succeeded on ALL ranks the exchange is switched off everywhere and the
+        statistics travel by the group's all-reduce (a rank pushing into peer memory while another
+        waits in an NCCL all-reduce would hang both).  Returns a description of the transport."""
+        from . import ops
+        err = ""
+        try:
+            cls.enable(group)
+        except Exception as exc:  # noqa: BLE001 - any failure selects the NCCL transport
+            err = f"{type(exc).__name__}: {exc}"
+        g = dist.group.WORLD if group is None else group
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(g) == "nccl" else "cpu"
+        okf = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN, group=g)
+        if int(okf.item()) == 1:
+            return "one-kernel push exchange over NVLink peer memory (symmetric memory)"
+        ops.set_peer_exchange(ops.register_group(g), None)
+        return ("NCCL all-reduce (peer memory unavailable on at least one rank"
+                + (f"; here: {err}" if err else "") + ")")[:200]
 
     def allreduce_(self, stats: torch.Tensor) -> torch.Tensor:
         """In-place SUM of an fp64 device vector over the group (the op the kernels use)."""

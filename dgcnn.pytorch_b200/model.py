@@ -15,6 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .dgcnn import DGCNN
+from .syncbn import batch_norm_rows
 
 
 class ClsHead(nn.Module):
@@ -37,8 +38,10 @@ class ClsHead(nn.Module):
             # plain reductions (torch's adaptive max pool kernel is ~20x slower at N=1024)
             x = torch.cat((x.max(dim=-1)[0].view(b, -1), x.mean(dim=-1).view(b, -1)), 1)
         # else: already pooled, [B, 2*emb] (DGCNN.forward_pooled)
-        x = self.dp1(F.leaky_relu(self.bn6(self.linear1(x)), negative_slope=0.2))
-        x = self.dp2(F.leaky_relu(self.bn7(self.linear2(x)), negative_slope=0.2))
+        # bn6 / bn7: plain BatchNorm1d, or -- after SyncBatchNorm conversion -- the statistics exchange
+        # of the EdgeConv layers instead of torch's NCCL collectives (syncbn.py)
+        x = self.dp1(F.leaky_relu(batch_norm_rows(self.linear1(x), self.bn6), negative_slope=0.2))
+        x = self.dp2(F.leaky_relu(batch_norm_rows(self.linear2(x), self.bn7), negative_slope=0.2))
         return self.linear3(x)
 
 

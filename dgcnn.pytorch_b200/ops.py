@@ -94,18 +94,17 @@ def knn_op(x: Tensor, k: int, sorted: bool = True) -> Tensor:
     if k > MAX_K:
         raise RuntimeError(f"edgeconv_b200: k={k} exceeds the selector limit {MAX_K}")
     x = x.contiguous()
+    if knn_uses_tensor_cores(C, N, k):
+        # feature-space layers: tcgen05 / TMA distance tiles (knn_tc.cu)
+        hi, lo, xx = split_tf32_op(x)
+        return knn_tc_op(hi, lo, xx, B, N, k)
     with torch.cuda.device(x.device):
+        # xyz layer (and any shape the tensor-core kernel does not take): FP32 FMA tiles
         xx = torch.empty(B * N, device=x.device, dtype=torch.float32)
         idx = torch.empty(B, N, k, device=x.device, dtype=torch.int32)
         st = _stream(x)
-        if knn_uses_tensor_cores(C, N, k):
-            # feature-space layers: tcgen05 / TMA distance tiles (knn_tc.cu)
-            hi, lo, xx = split_tf32_op(x)
-            return knn_tc_op(hi, lo, xx, B, N, k)
-        else:
-            # xyz layer (and any shape the tensor-core kernel does not take): FP32 FMA tiles
-            _lib.call("ecb200_sqnorms", _ptr(x), B, C, N, _ptr(xx), st)
-            _lib.call("ecb200_knn", _ptr(x), _ptr(xx), B, C, N, k, int(sorted), _ptr(idx), st)
+        _lib.call("ecb200_sqnorms", _ptr(x), B, C, N, _ptr(xx), st)
+        _lib.call("ecb200_knn", _ptr(x), _ptr(xx), B, C, N, k, int(sorted), _ptr(idx), st)
     return idx
 
 
@@ -152,13 +151,11 @@ def _(hi, lo, xx, B, N, k):
 
 def knn_uses_tensor_cores(C: int, N: int, k: int) -> bool:
     """Kernel choice for knn(): tensor cores where the contraction is a real GEMM
-    (C a multiple of 32 in [32, 128], k <= 40), FP32 FMA otherwise.  ECB200_KNN=fma|tc
-    overrides for A/B tests (tc still requires a supported shape)."""
-    mode = os.environ.get("ECB200_KNN", "auto")
-    supported = C % 32 == 0 and 32 <= C <= 128 and k <= 40
-    if mode == "fma":
+    (C a multiple of 32 in [32, 128], k <= 40), FP32 FMA otherwise (any C, k <= 64).
+    ECB200_KNN=fma forces the FMA kernel (A/B tests)."""
+    if os.environ.get("ECB200_KNN", "auto") == "fma":
         return False
-    return supported
+    return C % 32 == 0 and 32 <= C <= 128 and k <= 40
 
 
 def debug_tc_scores(x: Tensor) -> Tensor:
@@ -614,3 +611,29 @@ def embed_pool(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor, running_m
     if update_running:
         bn_update_running_op(res[3].detach(), running_mean, running_var, num_batches_tracked, mom)
     return res[0]
+
+
+# ------------------------------------------------------------------------- autocast
+# Under torch.autocast (main_partseg_dist.py:253) the reference's bmm / conv2d would run in fp16
+# while its pow/sum and BatchNorm statistics stay fp32.  The fused path always
+# computes in fp32 (3xTF32 on the tensor cores): every op casts its floating-point inputs to fp32
+# and runs with autocast disabled.  Gradients are linear in the incoming gradient, so GradScaler's
+# loss scaling and its inf/nan detection pass through unchanged.
+for _op in (knn_op, split_tf32_op, knn_tc_op, graph_feature_op, graph_feature_bwd_op, edgeconv_fwd_op,
+            edgeconv_bwd_op, embed_pool_fwd_op, embed_pool_bwd_op):
+    _op.register_autocast("cuda", torch.float32)
+
+
+def check_neighbour_indices(idx: Tensor, B: int, N: int) -> Tensor:
+    """Validate caller-supplied neighbour indices (shape [B,N,k], 0 <= idx < N) and return them as
+    contiguous int32.  The kernels index device memory with them unchecked, where the reference's
+    advanced indexing (dgcnn.py:33) would raise; the range check is asynchronous (device-side
+    assert) and skipped while a CUDA graph is being captured."""
+    if idx.dim() != 3 or idx.shape[0] != B or idx.shape[1] != N:
+        raise ValueError(f"edgeconv_b200: idx must have shape [{B}, {N}, k], got {tuple(idx.shape)}")
+    if idx.dtype not in (torch.int32, torch.int64):
+        raise TypeError(f"edgeconv_b200: idx must be int32 or int64, got {idx.dtype}")
+    if idx.is_cuda and not torch.cuda.is_current_stream_capturing():
+        lo, hi = torch.aminmax(idx)
+        torch._assert_async((lo >= 0) & (hi < N), "edgeconv_b200: neighbour index out of range [0, N)")
+    return idx.to(torch.int32).contiguous()

@@ -1,0 +1,207 @@
+"""Boundary tests on the GPU (-m gpu): the drop-in under the reference's own callers and runtimes.
+
+* the reference's ``PositionEmbedding`` (models/layers.py) and ``Net`` (models/model_partseg.py),
+  loaded UNMODIFIED from baseline/_ref, run on top of the drop-in ``models.dgcnn`` and are compared
+  with the same modules on top of the reference's own ``models/dgcnn.py`` (eager torch on the GPU,
+  TF32 off) -- same weights, same inputs;
+* ``torch.autocast`` + ``GradScaler`` as main_partseg_dist.py:221,253-265 uses them: the ops run in
+  fp32 under autocast, loss scaling passes through the backward linearly, inf gradients are seen by
+  the scaler;
+* two host threads driving two independent models concurrently (``nn.DataParallel`` style,
+  main_cls.py:62): the C ABI is re-entrant.
+Skipped when baseline/_ref has not been installed (python baseline/install_ref.py).
+"""
+import os
+import sys
+import threading
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "baseline"))
+import ref_cls  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not ref_cls.available(), reason="baseline/_ref not installed")
+
+
+@pytest.fixture(scope="module")
+def ec():
+    import dgcnn_pytorch_b200 as ec
+    return ec
+
+
+@pytest.fixture(autouse=True)
+def _fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _dropin_module(ec):
+    import types
+    m = types.ModuleType("dropin_models_dgcnn")
+    m.knn, m.get_graph_feature, m.DGCNN = ec.knn, ec.get_graph_feature, ec.DGCNN
+    return m
+
+
+def rel_err(a, b):
+    return ((a.detach().double() - b.detach().double()).abs().max() / b.detach().double().abs().max().clamp_min(1e-30)).item()
+
+
+@needs_ref
+def test_reference_position_embedding_on_dropin(ec):
+    from dgcnn_pytorch_b200.synthetic import synthetic_xyz
+    ref_layers, _ = ref_cls.reference_stack(ref_cls.reference_dgcnn_module(), "ref")
+    our_layers, _ = ref_cls.reference_stack(_dropin_module(ec), "ours")
+    args = SimpleNamespace(k=12)
+    torch.manual_seed(0)
+    a = ref_layers.PositionEmbedding(args).to(dev()).train()
+    b = our_layers.PositionEmbedding(args).to(dev()).train()
+    # the reference zero-initialises the 3x3 head; randomise it so gradients reach the edge block
+    torch.nn.init.normal_(a.transform.weight, std=0.05)
+    b.load_state_dict(a.state_dict())
+    x = synthetic_xyz(4, 256, seed=2).to(dev())
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = a(xa), b(xb)
+    assert rel_err(yb, ya) < 1e-4
+    w = torch.randn_like(ya)
+    (ya * w).sum().backward()
+    (yb * w).sum().backward()
+    assert rel_err(xb.grad, xa.grad) < 2e-3
+    for (n, p), (_, q) in zip(b.named_parameters(), a.named_parameters()):
+        if q.grad is not None and q.grad.abs().max() > 1e-6:
+            assert rel_err(p.grad, q.grad) < 2e-3, n
+
+
+@needs_ref
+def test_reference_partseg_net_on_dropin(ec, monkeypatch):
+    from dgcnn_pytorch_b200.synthetic import synthetic_xyz
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    _, ref_ps = ref_cls.reference_stack(ref_cls.reference_dgcnn_module(), "ref")
+    _, our_ps = ref_cls.reference_stack(_dropin_module(ec), "ours")
+    args = SimpleNamespace(k=8, emb_dim=64, n_heads=2, n_blocks=1, ff_dims=128, dropout=0.0, nclasses=50)
+    torch.manual_seed(0)
+    a = ref_ps.Net(args).to(dev()).eval()
+    b = our_ps.Net(args).to(dev()).eval()
+    b.load_state_dict(a.state_dict())            # same keys: the drop-in DGCNN has the reference's state_dict
+    x = synthetic_xyz(2, 256, seed=4).to(dev())
+    lbl = torch.zeros(2, 16, device=dev())
+    lbl[0, 3] = lbl[1, 7] = 1.0
+    with torch.no_grad():
+        ya, yb = a(x, lbl), b(x, lbl)
+    assert ya.shape == yb.shape == (2, 50, 256)
+    # compute_hog_1x1 truncates angles with .int(): a neighbour-order change can move a vote across a
+    # bin edge for an isolated point, so require 99.5 % of the logits within 1e-3 of the scale
+    close = ((ya - yb).abs() <= 1e-3 * ya.abs().max()).float().mean().item()
+    assert close >= 0.995, close
+
+
+def test_autocast_and_gradscaler(ec):
+    from dgcnn_pytorch_b200.synthetic import synthetic_xyz
+    torch.manual_seed(0)
+    args = SimpleNamespace(emb_dims=64, k=8, dropout=0.0)
+    net = ec.DGCNN_cls(args).to(dev()).train()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = synthetic_xyz(4, 128, seed=1).to(dev())
+    y = torch.tensor([1, 5, 7, 9], device=dev())
+    # fp32 run
+    loss32 = ec.cal_loss(net(x), y)
+    loss32.backward()
+    g32 = {n: p.grad.clone() for n, p in net.named_parameters()}
+    # autocast + GradScaler run from the same state (main_partseg_dist.py:253-265)
+    net.load_state_dict(sd)
+    net.zero_grad(set_to_none=True)
+    opt = torch.optim.SGD(net.parameters(), lr=0.0)
+    scaler = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = net(x)
+        loss16 = ec.cal_loss(out.float(), y)
+        # the ops themselves accept half inputs under autocast and answer in fp32
+        idx = ec.knn(x.half(), 8)
+        gf = ec.get_graph_feature(x.half(), k=8)
+        assert gf.dtype == torch.float32 and idx.dtype == torch.int64
+    scaler.scale(loss16).backward()
+    # EdgeConv gradients are the fp32 ones times the loss scale (the head's linears ran in fp16)
+    for n, p in net.named_parameters():
+        if n.startswith("backbone.conv") and g32[n].abs().max() > 1e-6:
+            assert rel_err(p.grad / 1024.0, g32[n]) < 3e-2, n
+    scaler.step(opt)
+    scaler.update()
+    assert scaler.get_scale() == 1024.0            # finite gradients: the scale is kept
+    # inf passthrough: an overflowing loss must surface as non-finite gradients so the scaler skips
+    net.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        loss = ec.cal_loss(net(x).float(), y)
+    (loss * float("inf")).backward()
+    w = net.backbone.conv2[0].weight.grad
+    assert not torch.isfinite(w).all()
+    scaler2 = torch.amp.GradScaler("cuda", init_scale=1024.0)
+    net.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        loss = ec.cal_loss(net(x).float(), y)
+    scaler2.scale(loss * 1e38).backward()
+    scaler2.step(opt)
+    scaler2.update()
+    assert scaler2.get_scale() < 1024.0            # the step was skipped and the scale backed off
+
+
+def test_two_host_threads_are_reentrant(ec):
+    """nn.DataParallel drives one Python thread per replica (main_cls.py:62); here two threads run
+    two independent models on their own streams concurrently and must reproduce the serial results."""
+    from dgcnn_pytorch_b200.synthetic import synthetic_xyz
+    args = SimpleNamespace(emb_dims=64, k=10, dropout=0.0)
+    torch.manual_seed(0)
+    nets = [ec.DGCNN_cls(args).to(dev()).train() for _ in range(2)]
+    xs = [synthetic_xyz(3, 192, seed=s).to(dev()) for s in (11, 12)]
+    ys = [torch.tensor([1, 2, 3], device=dev()), torch.tensor([4, 5, 6], device=dev())]
+    sds = [{k: v.clone() for k, v in n.state_dict().items()} for n in nets]
+
+    def run(i, out, stream=None):
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())
+        with ctx:
+            for _ in range(5):
+                nets[i].load_state_dict(sds[i])
+                nets[i].zero_grad(set_to_none=True)
+                loss = ec.cal_loss(nets[i](xs[i]), ys[i])
+                loss.backward()
+            out[i] = (loss.detach().clone(), [p.grad.clone() for p in nets[i].parameters()])
+        torch.cuda.synchronize()
+
+    serial, threaded = {}, {}
+    for i in range(2):
+        run(i, serial)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    errs = []
+
+    def guarded(i):
+        try:
+            run(i, threaded, streams[i])
+        except Exception as exc:  # noqa: BLE001
+            errs.append(exc)
+    ts = [threading.Thread(target=guarded, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i in range(2):
+        assert torch.allclose(serial[i][0], threaded[i][0], rtol=1e-5, atol=1e-6)
+        for gs, gt in zip(serial[i][1], threaded[i][1]):
+            assert rel_err(gt, gs) < 1e-4
+
+
+def test_external_idx_is_validated(ec):
+    from dgcnn_pytorch_b200.synthetic import synthetic_features
+    x = synthetic_features(1, 4, 16, seed=1).to(dev())
+    with pytest.raises(ValueError):
+        ec.get_graph_feature(x, k=4, idx=torch.zeros(1, 15, 4, dtype=torch.int64, device=dev()))
+    with pytest.raises(TypeError):
+        ec.get_graph_feature(x, k=4, idx=torch.zeros(1, 16, 4, device=dev()))

@@ -1,28 +1,55 @@
 """torchrun --nproc-per-node N tools/check_ddp_equivalence.py
 
 Sharded training step == single-GPU step on the whole batch: every rank runs DGCNN_cls
-(SyncBatchNorm semantics, BatchNorm statistics over NVLink peer memory, FlatGradSync) on its
-shard of a global batch; rank 0 also runs the same weights in one process on the full batch with
-plain BatchNorm.  Loss, averaged gradients and BatchNorm running statistics must agree."""
-import os, sys
+(SyncBatchNorm semantics, BatchNorm statistics exchanged between gather and finalize, FlatGradSync) on
+its shard of a global batch; rank 0 also runs the same weights in one process on the full batch with
+plain BatchNorm.  Loss, averaged gradients and BatchNorm running statistics must agree.
+
+Environment:
+  DDP_CHECK_BACKEND  nccl (default: one GPU per rank, statistics over NVLink peer memory) |
+                     gloo (ranks may SHARE a GPU -- rank r uses cuda:(r % device_count) -- so the
+                     world-size-N protocol is checked on a one-GPU box; statistics travel by gloo)
+  DDP_CHECK_B        global batch (default 4 * world);  DDP_CHECK_N, DDP_CHECK_K, DDP_CHECK_EMB
+  DDP_CHECK_ARBITER  1: rank 0 also runs the fp64 CPU oracle on the same graphs and reports the
+                     deviation of BOTH the sharded and the full-batch GPU gradients from it
+  DDP_CHECK_VERBOSE  1: per-parameter table
+  DDP_CHECK_OUT      path of a JSON result file (rank 0)
+"""
+import json
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
-from types import SimpleNamespace
-import torch
-import torch.distributed as dist
-import dgcnn_pytorch_b200 as ec
-import edgeconv_oracle as orc
-from dgcnn_pytorch_b200.dist import FlatGradSync, PeerStatsExchange, shard_range
+from types import SimpleNamespace  # noqa: E402
 
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import dgcnn_pytorch_b200 as ec  # noqa: E402
+import edgeconv_oracle as orc  # noqa: E402  (this is a checker, not the product)
+from dgcnn_pytorch_b200.dist import FlatGradSync, PeerStatsExchange, shard_range  # noqa: E402
+
+backend = os.environ.get("DDP_CHECK_BACKEND", "nccl")
 local = int(os.environ.get("LOCAL_RANK", "0"))
-torch.cuda.set_device(local)
-dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+ndev = torch.cuda.device_count()
+if backend == "nccl":
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+else:
+    dev = torch.device("cuda", local % ndev)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
-B, N, k = int(os.environ.get("DDP_CHECK_B", 4 * world)), 256, 12
-args = SimpleNamespace(emb_dims=128, k=k, dropout=0.0)
+B = int(os.environ.get("DDP_CHECK_B", 4 * world))
+N = int(os.environ.get("DDP_CHECK_N", 256))
+k = int(os.environ.get("DDP_CHECK_K", 12))
+emb = int(os.environ.get("DDP_CHECK_EMB", 128))
+verbose = bool(os.environ.get("DDP_CHECK_VERBOSE"))
+args = SimpleNamespace(emb_dims=emb, k=k, dropout=0.0)
 torch.manual_seed(3)
 ref = ec.DGCNN_cls(args).to(dev).train()                      # identical on every rank (same seed)
 sd = {n: v.clone() for n, v in ref.state_dict().items()}
@@ -33,8 +60,9 @@ y = torch.randint(0, 40, (B + off,), generator=torch.Generator().manual_seed(5))
 model = ec.DGCNN_cls(args).to(dev)
 model.load_state_dict(sd)
 model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model).train()
-sync = FlatGradSync(model.parameters(), overlap=os.environ.get("ECB200_GRAD_OVERLAP", "1") == "1")
-mode = os.environ.get("ECB200_STATS_EXCHANGE", "peer")
+sync = FlatGradSync(model.parameters(), overlap=os.environ.get("ECB200_GRAD_OVERLAP", "1") == "1"
+                    and backend == "nccl")
+mode = os.environ.get("ECB200_STATS_EXCHANGE", "peer") if backend == "nccl" else "gloo all-reduce"
 if mode == "peer":
     PeerStatsExchange.enable()
 b0, b1 = shard_range(B, world, rank)
@@ -44,32 +72,17 @@ sync.zero()
 logits = model(x[b0:b1])
 loss = ec.cal_loss(logits, y[b0:b1])
 loss.backward()
-if os.environ.get("DDP_CHECK_VERBOSE"):
-    # per-rank forward check against the full-batch reference, and the all-reduce against a
-    # manual mean of the gathered per-rank gradients
-    with torch.no_grad():
-        sdr = {n: v.clone() for n, v in ref.state_dict().items()}
-        full = ref(x)
-        ref.load_state_dict(sdr)
-    fdev = ((logits.detach() - full[b0:b1]).abs().max() / full.abs().max()).reshape(1)
-    fall = [torch.empty_like(fdev) for _ in range(world)]
-    dist.all_gather(fall, fdev)
-    gath = [torch.empty_like(sync.flat) for _ in range(world)]
-    dist.all_gather(gath, sync.flat)
-    manual = torch.stack(gath).mean(0)
 sync.average()
-if os.environ.get("DDP_CHECK_VERBOSE") and rank == 0:
-    print("    per-rank logits deviation vs full-batch reference:", [f"{float(v):.1e}" for v in fall], flush=True)
-    print(f"    all-reduce vs manual mean of gathered grads: {((sync.flat - manual).abs().max() / manual.abs().max()).item():.2e}",
-          flush=True)
 gl = loss.detach().clone()
 dist.all_reduce(gl)
 gl /= world
 ok = True
 if rank == 0:
+    ref.backbone.record_idx = True
     ref.zero_grad(set_to_none=True)
     lr = ec.cal_loss(ref(x), y)
     lr.backward()
+
     def rel(a, b):
         return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
     devs = [("loss", abs(gl.item() - lr.item()) / abs(lr.item()), abs(lr.item()))]
@@ -82,12 +95,44 @@ if rank == 0:
             devs.append((f"buffer {n}", rel(bp, bq), bq.abs().max().item()))
     devs.sort(key=lambda t: -t[1])
     worst = devs[0]
-    if os.environ.get("DDP_CHECK_VERBOSE"):
+    if verbose:
         for n, r, sc in devs[:8]:
             print(f"    {n:40s} rel {r:.2e}  (scale {sc:.2e})", flush=True)
+    result = {"world": world, "backend": backend, "stats_exchange": mode, "B": B, "N": N, "k": k, "emb": emb,
+              "worst": {"name": worst[0], "rel": worst[1]}, "tolerance": 2e-4}
+    if os.environ.get("DDP_CHECK_ARBITER"):
+        # fp64 CPU oracle on the graphs the full-batch GPU run used: which side is off?
+        o = orc.DGCNNClsOracle(args).double().train()
+        o.load_state_dict({n: v.detach().cpu().double() if v.dtype.is_floating_point else v.detach().cpu()
+                           for n, v in sd.items()})
+        idx_list = [i.long().cpu() for i in ref.backbone.last_idx]
+        lo = orc.smoothed_ce_oracle(o(x.cpu().double(), idx_list=idx_list), y.cpu())
+        lo.backward()
+        worst_s = worst_f = ("", 0.0)
+        for (n, p), (_, q), (_, r) in zip(model.named_parameters(), ref.named_parameters(), o.named_parameters()):
+            if r.grad.abs().max().item() < 1e-6:
+                continue
+            ds, df = rel(p.grad.cpu().double(), r.grad), rel(q.grad.cpu().double(), r.grad)
+            if ds > worst_s[1]:
+                worst_s = (n, ds)
+            if df > worst_f[1]:
+                worst_f = (n, df)
+            if verbose:
+                print(f"    vs fp64 oracle  {n:32s} sharded {ds:.2e}   full-batch {df:.2e}", flush=True)
+        print(f"  fp64-oracle arbiter: sharded worst {worst_s[1]:.2e} ({worst_s[0]}), full-batch GPU worst "
+              f"{worst_f[1]:.2e} ({worst_f[0]})", flush=True)
+        result["vs_fp64_oracle"] = {"sharded": worst_s[1], "full_batch": worst_f[1]}
     ok = worst[1] < 2e-4
-    print(f"ddp equivalence ({world} ranks, stats exchange = {mode}, overlap = "
-          f"{os.environ.get('ECB200_GRAD_OVERLAP', '1')}): worst relative deviation "
-          f"{worst[1]:.2e} at {worst[0]} -> {'OK' if ok else 'FAIL'}", flush=True)
-dist.barrier(); torch.cuda.synchronize()
-os._exit(0 if ok else 1)
+    result["ok"] = ok
+    print(f"ddp equivalence ({world} ranks, backend {backend}, stats exchange = {mode}, B={B} N={N} k={k}): "
+          f"worst relative deviation {worst[1]:.2e} at {worst[0]} -> {'OK' if ok else 'FAIL'}", flush=True)
+    if os.environ.get("DDP_CHECK_OUT"):
+        with open(os.environ["DDP_CHECK_OUT"], "a") as f:
+            f.write(json.dumps(result) + "\n")
+flag = torch.tensor([1 if ok else 0])
+if backend == "nccl":
+    flag = flag.to(dev)
+dist.broadcast(flag, 0)
+dist.barrier()
+torch.cuda.synchronize()
+os._exit(0 if int(flag.item()) else 1)
