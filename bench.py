@@ -314,7 +314,7 @@ EDGE_FWD_KERNELS = ("knn_tc_kernel", "knn_xyz_kernel", "knn_fma_kernel", "sqnorm
 
 def short_kernel_name(name):
     """'void <unnamed>::knn_tc_kernel<32, 0>(const float*, ...)' -> 'knn_tc_kernel<32, 0>'"""
-    n = name
+    n = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
     if n.startswith("void "):
         n = n[5:]
     depth, out = 0, []
@@ -326,8 +326,7 @@ def short_kernel_name(name):
         elif ch == "(" and depth == 0:
             break
         out.append(ch)
-    n = "".join(out).replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
-    return n[:96]
+    return "".join(out)[:96]
 
 
 def profile_graph_kernels(replay, nsteps):
@@ -348,6 +347,8 @@ def profile_graph_kernels(replay, nsteps):
             dur = getattr(ev, "device_time", None)
             if dur is None:
                 dur = getattr(ev, "cuda_time", 0.0)
+            if "FillFunctor<unsigned char>" in ev.name:
+                continue          # the L2 flush between the replays, not part of the step
             d = agg.setdefault(short_kernel_name(ev.name), [0, 0.0])
             d[0] += 1
             d[1] += float(dur)

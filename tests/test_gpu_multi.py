@@ -44,8 +44,10 @@ def _run(world, backend, tmp_path, extra_env=None, timeout=600):
     assert r.returncode == 0, f"{backend} x{world} failed:\n{tail}"
     res = json.loads(out.read_text().strip().splitlines()[-1])
     assert res["ok"] and res["world"] == world, res
-    # both sides also agree with the fp64 oracle run on the same graphs
-    assert res["vs_fp64_oracle"]["sharded"] < 5e-4 and res["vs_fp64_oracle"]["full_batch"] < 5e-4, res
+    # both sides also agree with the fp64 oracle run on the same graphs (looser: against fp64 an
+    # EdgeConv activation within fp32 rounding of the LeakyReLU kink, or a tied max, may resolve the
+    # other way -- the sharded and the full-batch GPU runs share their rounding and agree to ~1e-5)
+    assert res["vs_fp64_oracle"]["sharded"] < 5e-3 and res["vs_fp64_oracle"]["full_batch"] < 5e-3, res
     return res
 
 

@@ -12,7 +12,17 @@ Environment:
   DDP_CHECK_B        global batch (default 4 * world);  DDP_CHECK_N, DDP_CHECK_K, DDP_CHECK_EMB
   DDP_CHECK_ARBITER  1: rank 0 also runs the fp64 CPU oracle on the same graphs and reports the
                      deviation of BOTH the sharded and the full-batch GPU gradients from it
+  DDP_CHECK_SEED     data seed (default: scan 5, 6, ... for the first batch without a knife-edge, below)
   DDP_CHECK_VERBOSE  1: per-parameter table
+
+Knife-edge rule.  LeakyReLU is not differentiable at 0: an activation whose pre-activation is within
+fp32 rounding of 0 gets derivative 1 or 0.2 depending on the last bit, in ANY implementation (the
+reference included), and the head's BatchNorm bias starts at 0, so its pre-activation IS the
+normalised value.  With the historical data seed 5 and B = 32 one element of bn6's output has
+|y| ~ 1e-8: single-GPU, sharded and fp64 runs then differ by 1-15 % in head.bn6.bias and everything
+upstream of it while every forward value agrees to 2e-6 (profiles/r2_ddp_equivalence.md).  The check
+therefore runs on the first seed whose head pre-activations all satisfy |y| > 1e-4 (reported as
+"kink margin"); DDP_CHECK_SEED=5 reproduces the knife-edge case.
   DDP_CHECK_OUT      path of a JSON result file (rank 0)
 """
 import json
@@ -54,8 +64,43 @@ torch.manual_seed(3)
 ref = ec.DGCNN_cls(args).to(dev).train()                      # identical on every rank (same seed)
 sd = {n: v.clone() for n, v in ref.state_dict().items()}
 off = int(os.environ.get("DDP_CHECK_OFFSET", "0"))     # clouds [off, off+B) of a larger batch
-x = orc.synthetic_xyz(B + off, N, seed=5)[off:].contiguous().to(dev)
-y = torch.randint(0, 40, (B + off,), generator=torch.Generator().manual_seed(5))[off:].to(dev)
+
+
+def batch(seed):
+    xs = orc.synthetic_xyz(B + off, N, seed=seed)[off:].contiguous().to(dev)
+    ys = torch.randint(0, 40, (B + off,), generator=torch.Generator().manual_seed(seed))[off:].to(dev)
+    return xs, ys
+
+
+def kink_margin(xs):
+    """min |pre-activation| over the head's two LeakyReLUs in a full-batch forward (rank 0)."""
+    seen = []
+    hooks = [m.register_forward_hook(lambda _m, _i, o: seen.append(o.detach().abs().min().item()))
+             for m in (ref.head.bn6, ref.head.bn7)]
+    with torch.no_grad():
+        ref(xs)
+    for h in hooks:
+        h.remove()
+    ref.load_state_dict(sd)          # undo the running-statistics update of this probe
+    return min(seen)
+
+
+seed_t = torch.zeros(2, dtype=torch.float64)
+if rank == 0:
+    if os.environ.get("DDP_CHECK_SEED"):
+        seed = int(os.environ["DDP_CHECK_SEED"])
+        margin = kink_margin(batch(seed)[0])
+    else:
+        for seed in range(5, 64):
+            margin = kink_margin(batch(seed)[0])
+            if margin > 1e-4:
+                break
+    seed_t[0], seed_t[1] = seed, margin
+if backend == "nccl":
+    seed_t = seed_t.to(dev)
+dist.broadcast(seed_t, 0)
+seed, margin = int(seed_t[0].item()), float(seed_t[1].item())
+x, y = batch(seed)
 
 model = ec.DGCNN_cls(args).to(dev)
 model.load_state_dict(sd)
@@ -99,6 +144,7 @@ if rank == 0:
         for n, r, sc in devs[:8]:
             print(f"    {n:40s} rel {r:.2e}  (scale {sc:.2e})", flush=True)
     result = {"world": world, "backend": backend, "stats_exchange": mode, "B": B, "N": N, "k": k, "emb": emb,
+              "seed": seed, "kink_margin": margin,
               "worst": {"name": worst[0], "rel": worst[1]}, "tolerance": 2e-4}
     if os.environ.get("DDP_CHECK_ARBITER"):
         # fp64 CPU oracle on the graphs the full-batch GPU run used: which side is off?
@@ -124,7 +170,8 @@ if rank == 0:
         result["vs_fp64_oracle"] = {"sharded": worst_s[1], "full_batch": worst_f[1]}
     ok = worst[1] < 2e-4
     result["ok"] = ok
-    print(f"ddp equivalence ({world} ranks, backend {backend}, stats exchange = {mode}, B={B} N={N} k={k}): "
+    print(f"ddp equivalence ({world} ranks, backend {backend}, stats exchange = {mode}, B={B} N={N} k={k}, "
+          f"data seed {seed}, head kink margin {margin:.1e}): "
           f"worst relative deviation {worst[1]:.2e} at {worst[0]} -> {'OK' if ok else 'FAIL'}", flush=True)
     if os.environ.get("DDP_CHECK_OUT"):
         with open(os.environ["DDP_CHECK_OUT"], "a") as f:
