@@ -16,6 +16,8 @@
 #include <cuda.h>
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -31,27 +33,57 @@ constexpr int BM = 128;                  // query rows per CTA (= TMEM lanes)
 constexpr int BN = 128;                  // candidates per MMA tile (= TMEM columns per stage)
 constexpr int KB = 32;                   // channels per K-block: 32 fp32 = one 128-byte swizzle row
 constexpr int TILE_BYTES = BM * KB * 4;  // 16 KB: one K-block of one operand half
+constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // a ring stage: (hi | lo) of a K-block, or two hi K-blocks
 constexpr int MAX_KB = 4;                // C <= 128 keeps the query tile resident
 constexpr int NUM_EPI = 128;             // threads per epilogue warpgroup (one per TMEM lane)
 constexpr int NT = 64 + 2 * NUM_EPI;     // producer warp + MMA warp + two epilogue warpgroups
+constexpr int LS = 2 * NUM_EPI;          // stride (in entries) between a thread's consecutive survivor slots
 constexpr uint32_t TMEM_COLS = 512;      // two accumulator stages (2 x 128 columns) + the query tile
 constexpr uint32_t A_COL0 = 2 * BN;      // hi at columns [256, 256+C), lo at [256+C, 256+2C)
-constexpr int NSTAGE = 5;                // B ring: 5 x 32 KB; the final ranking reuses these 160 KB
 constexpr int UMMA_K = 8;                // tf32: 32 bytes of K per instruction
 constexpr int KMAX = 40;                 // largest k this kernel takes
+constexpr int GUARD = 16;                // candidate columns between two overflow checks of a survivor list
 
-struct SharedTail {  // lives after the operand tiles
-  float hx[2][2][BN];          // [group][ping-pong] -0.5*|x_j|^2 of the current column tile
-  float stage_s[16][2 * NUM_EPI];  // exchange of the sorted bins between the two threads of a row
+struct SharedTail {  // lives after the operand ring and the survivor lists
+  float hx[2][2][BN];              // [group][ping-pong] -0.5*|x_j|^2 of the current column tile
   int cnt_x[2][NUM_EPI];           // survivor-count exchange between the two threads of a row
+  int sum_x[2][NUM_EPI];           // sum of the score-only ranks of a thread's entries (tie detection)
   float xmax_w[2 * NUM_EPI / 32];  // per-warp max |x_j|^2 over the candidates it staged
-  uint64_t a_full, b_full[NSTAGE], b_empty[NSTAGE], t_full[2], t_empty[2];
+  uint64_t a_full, b_full[8], b_empty[8], t_full[2], t_empty[2];
   uint32_t tmem_slot;
 };
 
-// the B ring (NSTAGE x 32 KB = 160 KB) is reused by the final ranking: cap * 256 keys * 8 bytes
-__host__ __device__ constexpr size_t smem_bytes() {
-  return 1024 /* alignment slack */ + (size_t)(2 * NSTAGE) * TILE_BYTES + sizeof(SharedTail);
+// shared memory: [S ring stages of 32 KB][cap survivor slots x 256 threads x 8 bytes][tail]
+__host__ __device__ constexpr size_t smem_bytes(int S, int cap) {
+  return 1024 /* alignment slack */ + (size_t)S * STAGE_BYTES + (size_t)cap * LS * sizeof(uint64_t) +
+         sizeof(SharedTail);
+}
+
+// ---- cluster helpers (TMA multicast of the candidate tiles between the CTAs of one cloud) ----------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the box lands at the same CTA-relative offset in every CTA of `mask`, and completes `bar` there
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` of every CTA in `mask` when they complete
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
 }
 
 template <int NBINS>
@@ -74,16 +106,15 @@ __device__ __forceinline__ void sort_bins_desc(float (&v)[NBINS]) {
   }
 }
 
-// Overflow of a thread's survivor list (only with massive ties or clustered data): keep its own
-// best k keys in place and return the score a later candidate must reach to matter ("strictly
-// better than the k-th kept": later candidates of equal score have a larger j, hence a smaller
-// key).  Out of line and not unrolled: it must not bloat the hot loop's instruction footprint.
 // raw survivor entry (score bits << 32 | j) -> totally ordered key (larger score, then smaller j)
 __device__ __forceinline__ uint64_t ordered_key(uint64_t raw) {
   return make_key(__uint_as_float((uint32_t)(raw >> 32)), (int)(uint32_t)raw);
 }
+// Overflow of a thread's survivor list (only with massive ties or clustered data): keep its own
+// best k entries in place and return the score a later candidate must reach to matter ("strictly
+// better than the k-th kept": later candidates of equal score have a larger j, hence a smaller
+// key).  Out of line and not unrolled: it must not bloat the hot loop's instruction footprint.
 __device__ __noinline__ float shrink_survivors(uint64_t* buf, int cnt, int k) {
-  constexpr int LS = 2 * NUM_EPI;
 #pragma unroll 1
   while (cnt > k) {
     int arg = 0;
@@ -108,13 +139,17 @@ __device__ __noinline__ float shrink_survivors(uint64_t* buf, int cnt, int k) {
     if (tl && blockIdx.x == 0 && blockIdx.y == 0 && (i) < 256) tl[(role) * 256 + (i)] = clock64(); \
   } while (0)
 
-// DEBUG = true: one sweep, raw scores written to dbg[B,N,N] (validation of the MMA plumbing)
-template <int NBINS, bool DEBUG>
+// DEBUG = true: one sweep, raw scores written to dbg[B,N,N] (validation of the MMA plumbing; also
+//               the dense-store epilogue of the per-point GEMM)
+// CL:           CTAs per cluster.  The CL row tiles of a cluster belong to one cloud and stream the
+//               same candidate tiles: each CTA fetches 1/CL of every tile and TMA multicasts it to
+//               all of them, so the L2 -> SM traffic of the candidates drops by CL.
+// S:            ring stages of 32 KB.
+template <int NBINS, bool DEBUG, int CL, int S>
 __global__ void __launch_bounds__(NT, 1)
 knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g,
               const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-              const float* __restrict__ xx, int Na, int N, int nkb, int k,
-              uint64_t* __restrict__ surv_ws, int cap,
+              const float* __restrict__ xx, int Na, int N, int nkb, int k, int cap,
               int32_t* __restrict__ idx, float* __restrict__ dbg, long long* tl) {
   // A operand: rows [b*Na + rt*128, +128) of a_hi_g / a_lo_g [*, C] (the queries; for the GEMM use
   // the points), copied ONCE into tensor memory (lane = row, column = channel): the MMAs then
@@ -125,29 +160,48 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
   // 1024-byte alignment by pointer arithmetic on the __shared__ array (an integer round-trip
   // would turn every later access into a generic-address load/store)
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  constexpr int S = NSTAGE;
   const int C = nkb * KB;
-  unsigned char* b_st = base;                                  // [S][hi 16 KB | lo 16 KB]
-  SharedTail* T = reinterpret_cast<SharedTail*>(b_st + (size_t)S * 2 * TILE_BYTES);
+  unsigned char* b_st = base;                                  // [S][32 KB]
+  uint64_t* surv = reinterpret_cast<uint64_t*>(b_st + (size_t)S * STAGE_BYTES);   // [cap][256]
+  SharedTail* T = reinterpret_cast<SharedTail*>(reinterpret_cast<unsigned char*>(surv) +
+                                                (size_t)(DEBUG ? 0 : cap) * LS * sizeof(uint64_t));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, rt = blockIdx.x;
   const int nct = (N + BN - 1) / BN;
-  const int npass = DEBUG ? 1 : 2;
   const int cloud_row0 = b * N;   // first global B row of this cloud
   const int a_row0 = b * Na;      // first global A row of this cloud
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
+  // pass A multiplies the hi halves only: a stage then carries the hi halves of TWO K-blocks
+  const int kpa = (nkb & 1) ? 1 : 2;
+
+  // epilogue threads fetch their query row (first 64 channels) before anything else: the loads
+  // are in flight while the barriers are initialised and tensor memory is allocated
+  float4 pre[16];
+  if (warp >= 2) {
+    const int g = (warp - 2) >> 2, q = warp & 3;
+    const int row = rt * BM + q * 32 + lane;
+    const float* src = (g == 0 ? a_hi_g : a_lo_g) + (size_t)(a_row0 + row) * C;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      pre[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < Na && 4 * e < C) pre[e] = __ldg(reinterpret_cast<const float4*>(src) + e);
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&map_bhi);
     prefetch_tensormap(&map_blo);
     mbar_init(&T->a_full, 2 * NUM_EPI);
-    for (int s = 0; s < S; ++s) { mbar_init(&T->b_full[s], 1); mbar_init(&T->b_empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&T->b_full[s], 1); mbar_init(&T->b_empty[s], CL); }
     for (int s = 0; s < 2; ++s) { mbar_init(&T->t_full[s], 1); mbar_init(&T->t_empty[s], NUM_EPI); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&T->tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peers' barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = T->tmem_slot;
   if (threadIdx.x == 0) ECB_STAMP(5, 0);
@@ -160,67 +214,116 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
   }
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
-      int stage = 0;
+    // ===================== TMA producer (whole warp in the loop, one elected lane issues) =====
+    {
+      int stage = 0, n = 0;
       uint32_t phase = 0;
-      for (int pass = 0; pass < npass; ++pass)
+      constexpr int SLICE_ROWS = BM / CL;                 // rows of every tile this CTA fetches
+      const uint32_t slice_off = crank * (uint32_t)(SLICE_ROWS * KB * 4);
+      auto load = [&](unsigned char* dst, const CUtensorMap* m, uint64_t* bar, int c0, int r0) {
+        if (CL > 1) tma_load_2d_mc(dst + slice_off, m, bar, c0, r0 + (int)crank * SLICE_ROWS, CMASK);
+        else        tma_load_2d(dst, m, bar, c0, r0);
+      };
+      if (!DEBUG) {
         for (int ct = 0; ct < nct; ++ct)
-          for (int kb = 0; kb < nkb; ++kb) {
+          for (int kb = 0; kb < nkb; kb += kpa, ++n) {
             mbar_wait(&T->b_empty[stage], phase ^ 1);
-            ECB_STAMP(0, (pass * nct + ct) * nkb + kb);
-            unsigned char* dst = b_st + (size_t)stage * 2 * TILE_BYTES;
-            const bool need_lo = DEBUG || pass == 1;  // pass A multiplies the hi halves only
-            mbar_expect_tx(&T->b_full[stage], need_lo ? 2 * TILE_BYTES : TILE_BYTES);
-            tma_load_2d(dst, &map_bhi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
-            if (need_lo)
-              tma_load_2d(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+            if (elect_one_sync()) {
+              ECB_STAMP(0, n);
+              unsigned char* dst = b_st + (size_t)stage * STAGE_BYTES;
+              mbar_expect_tx(&T->b_full[stage], kpa * TILE_BYTES);
+              for (int j = 0; j < kpa; ++j)
+                load(dst + j * TILE_BYTES, &map_bhi, &T->b_full[stage], (kb + j) * KB, cloud_row0 + ct * BN);
+            }
+            __syncwarp();
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
+      }
+      for (int ct = 0; ct < nct; ++ct)
+        for (int kb = 0; kb < nkb; ++kb, ++n) {
+          mbar_wait(&T->b_empty[stage], phase ^ 1);
+          if (elect_one_sync()) {
+            ECB_STAMP(0, n);
+            unsigned char* dst = b_st + (size_t)stage * STAGE_BYTES;
+            mbar_expect_tx(&T->b_full[stage], 2 * TILE_BYTES);
+            load(dst, &map_bhi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+            load(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp in the loop, one elected lane issues) ========
+    {
       const uint32_t idesc = make_idesc_tf32(BM, BN);
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, T->tmem_slot, 0);   // warp-uniform by construction
       mbar_wait(&T->a_full, 0);
       tc_fence_after();
       int stage = 0;
       uint32_t phase = 0;
       int tile = 0;
-      const uint32_t ring_lo = sw128_kmajor_desc_lo(smem_u32(b_st));  // descriptor low word of stage 0, hi half
-      constexpr uint32_t STAGE_STEP = (2 * TILE_BYTES) >> 4, LO_STEP = TILE_BYTES >> 4, K8_STEP = (UMMA_K * 4) >> 4;
+      const uint32_t ring_lo = sw128_kmajor_desc_lo(smem_u32(b_st));  // descriptor low word of stage 0, first half
+      constexpr uint32_t STAGE_STEP = STAGE_BYTES >> 4, LO_STEP = TILE_BYTES >> 4, K8_STEP = (UMMA_K * 4) >> 4;
       const uint32_t a_col = tmem_base + A_COL0;
-      for (int pass = 0; pass < npass; ++pass) {
-        const bool three = DEBUG || pass == 1;  // pass A ranks with plain TF32 and an error margin
+      auto release = [&](int st) {  // frees the stage (in every CTA of the cluster) once these MMAs have read it
+        if (CL > 1) mma_commit_mc(&T->b_empty[st], CMASK);
+        else        mma_commit(&T->b_empty[st]);
+      };
+      if (!DEBUG) {
+        // pass A: plain TF32 on the hi halves (ranked with an error margin), two K-blocks per stage
         for (int ct = 0; ct < nct; ++ct, ++tile) {
           const int as = tile & 1;  // stage g is consumed by epilogue warpgroup g
           mbar_wait(&T->t_empty[as], ((tile >> 1) & 1) ^ 1);  // that group drained this stage
           tc_fence_after();
           ECB_STAMP(1, 2 * tile);
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-          for (int kb = 0; kb < nkb; ++kb) {
+          for (int kb = 0; kb < nkb; kb += kpa) {
             mbar_wait(&T->b_full[stage], phase);
             tc_fence_after();
-            const uint32_t ah = a_col + (uint32_t)(kb * KB);  // tensor-memory columns of A hi; lo at +C
             const uint32_t bh = ring_lo + (uint32_t)stage * STAGE_STEP;
-            if (three) {
+            if (elect_one_sync()) {
+              for (int j = 0; j < kpa; ++j) {
+                const uint32_t ah = a_col + (uint32_t)((kb + j) * KB);
 #pragma unroll
-              for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
-                mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, (kb | k8) != 0);
-                mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + LO_STEP + k8 * K8_STEP, idesc, 1);
-                mma_tf32_ts_lo(d_tmem, ah + (uint32_t)C + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, 1);
+                for (int k8 = 0; k8 < KB / UMMA_K; ++k8)
+                  mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + j * LO_STEP + k8 * K8_STEP, idesc, (kb | j | k8) != 0);
               }
-            } else {
-#pragma unroll
-              for (int k8 = 0; k8 < KB / UMMA_K; ++k8)
-                mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, (kb | k8) != 0);
+              release(stage);
+              if (kb + kpa >= nkb) mma_commit(&T->t_full[as]);  // accumulator ready for the epilogue
             }
-            mma_commit(&T->b_empty[stage]);  // frees the stage once these MMAs have read it
+            __syncwarp();
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
-          mma_commit(&T->t_full[as]);  // accumulator ready for the epilogue
           ECB_STAMP(1, 2 * tile + 1);
         }
+      }
+      // pass B (and the only sweep of the dense-store variant): 3xTF32, hi.hi + hi.lo + lo.hi
+      for (int ct = 0; ct < nct; ++ct, ++tile) {
+        const int as = tile & 1;
+        mbar_wait(&T->t_empty[as], ((tile >> 1) & 1) ^ 1);
+        tc_fence_after();
+        ECB_STAMP(1, 2 * tile);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&T->b_full[stage], phase);
+          tc_fence_after();
+          const uint32_t ah = a_col + (uint32_t)(kb * KB);  // tensor-memory columns of A hi; lo at +C
+          const uint32_t bh = ring_lo + (uint32_t)stage * STAGE_STEP;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
+              mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, (kb | k8) != 0);
+              mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + LO_STEP + k8 * K8_STEP, idesc, 1);
+              mma_tf32_ts_lo(d_tmem, ah + (uint32_t)C + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, 1);
+            }
+            release(stage);
+            if (kb + 1 == nkb) mma_commit(&T->t_full[as]);
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        ECB_STAMP(1, 2 * tile + 1);
       }
     }
   } else {
@@ -238,7 +341,21 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       // query rows -> tensor memory: group 0 copies the hi halves, group 1 the lo halves
       const float* src = (g == 0 ? a_hi_g : a_lo_g) + (size_t)(a_row0 + row) * C;
       const uint32_t dst = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + (uint32_t)(g * C);
-      for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {       // the prefetched first 64 channels
+        if (h * 32 < C) {
+          uint32_t r[32];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 f = pre[8 * h + e];
+            r[4 * e + 0] = __float_as_uint(f.x); r[4 * e + 1] = __float_as_uint(f.y);
+            r[4 * e + 2] = __float_as_uint(f.z); r[4 * e + 3] = __float_as_uint(f.w);
+          }
+          __syncwarp();
+          tmem_st_32x32(dst + (uint32_t)(h * 32), r);
+        }
+      }
+      for (int c0 = 64; c0 < C; c0 += 32) {
         uint32_t r[32];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -257,13 +374,15 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
     float bin[NBINS];
 #pragma unroll
     for (int u = 0; u < NBINS; ++u) bin[u] = -CUDART_INF_F;
-    // workspace layout is [tile][slot][group][row-in-tile]: for a fixed slot the 32 lanes of
-    // a warp (consecutive rows) touch consecutive words, so the traffic coalesces
-    const size_t tile_id = (size_t)b * gridDim.x + rt;
-    constexpr int LS = 2 * NUM_EPI;  // stride between a thread's consecutive slots
-    uint64_t* mybuf = surv_ws ? surv_ws + tile_id * (size_t)cap * LS + g * NUM_EPI + et : nullptr;
-    float* stage_s = &T->stage_s[0][g * NUM_EPI + et];
-    int cnt = 0;
+    // this thread's survivor list: column `me` of surv[cap][256]; consecutive lanes touch
+    // consecutive 8-byte words, so the (predicated) appends are conflict-free
+    const int me = g * NUM_EPI + et;
+    uint64_t* const sv = surv + me;
+    const uint32_t sv_addr = smem_u32(sv);
+    int cnt = 0;                  // entries in the list
+    constexpr uint32_t SLOT = LS * sizeof(uint64_t);   // bytes between consecutive slots
+    // |x_i|^2 for the pass-A margin: fetched now, needed after the first sweep
+    const float xi = (!DEBUG && xx && valid) ? __ldg(xx + cloud_row0 + row) : 0.f;
     float thr = CUDART_INF_F;
     float xmax = 0.f;  // max |x_j|^2 over the candidates this thread staged (for the pass-A margin)
     int use = 0;  // how many times this group has consumed its accumulator stage
@@ -278,7 +397,8 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
     // two passes get separate code (and register allocations: the bins die after the first)
     auto run_tiles = [&](auto pass_tag) {
       constexpr int pass = decltype(pass_tag)::value;
-      for (int ct = (pass * nct + g) & 1; ct < nct; ct += 2, ++use) {
+      const int tile0 = DEBUG ? 0 : pass * nct;
+      for (int ct = (tile0 + g) & 1; ct < nct; ct += 2, ++use) {
         float* hx = T->hx[g][use & 1];
         if (et == 0) ECB_STAMP(2 + g, 4 * use);
         {
@@ -333,21 +453,30 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
               bin[bi] = fmaxf(bin[bi], v[u]);
             }
           } else {
-            // One ballot per candidate column: the warp branches (uniformly) only for columns
-            // where some row keeps the candidate; those rows append (score bits, j) to their
-            // list in the L2-resident workspace.  Straight-line predicated code: no staging
-            // of the scores, no divergent loops.
-            if (valid && cnt + 32 > cap) {  // rare (ties, clustered data): keep the thread's own best k
-              thr = fmaxf(thr, shrink_survivors(mybuf, cnt, k));
-              cnt = min(cnt, k);
-            }
+            // Candidates that reach the row's threshold are appended to the thread's own list in
+            // shared memory: straight-line predicated code per candidate (compare, store, pointer
+            // bump), no votes, no branches, no dependence between rows.  Rows past the end of the
+            // cloud carry thr = +inf; masked columns score -inf.
             const int jb = ct * BN + c4 * 32;
 #pragma unroll
-            for (int u = 0; u < 32; ++u) {
-              const bool hit = valid && v[u] >= thr;
-              if (__any_sync(0xffffffffu, hit)) {
-                if (hit) {
-                  mybuf[cnt * LS] = ((uint64_t)__float_as_uint(v[u]) << 32) | (uint32_t)(jb + u);
+            for (int h = 0; h < 32 / GUARD; ++h) {
+              if (cnt > cap - GUARD) {  // rare (ties, clustered data): keep the thread's own best k
+                thr = fmaxf(thr, shrink_survivors(sv, cnt, k));
+                cnt = k;
+              }
+#pragma unroll
+              for (int u = h * GUARD; u < (h + 1) * GUARD; ++u) {
+                if (v[u] >= thr) {   // entry = (score bits << 32) | j
+                  // the slot address is formed in a scratch register per store: a running address
+                  // register would be rewritten right behind every (predicated) store that reads
+                  // it, and that write-after-read on a shared-memory store costs ~25 cycles
+                  asm volatile(
+                      "{\n\t"
+                      ".reg .u32 t;\n\t"
+                      "mad.lo.u32 t, %0, %1, %2;\n\t"
+                      "st.shared.v2.b32 [t], {%3, %4};\n\t"
+                      "}" ::"r"(cnt), "n"(SLOT), "r"(sv_addr), "r"(jb + u), "r"(__float_as_uint(v[u]))
+                      : "memory");
                   ++cnt;
                 }
               }
@@ -392,9 +521,7 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
           tc_fence_before();
           mbar_arrive(&T->t_empty[g]);
           process(r1, 1, true);
-          __syncwarp();
           process(r2, 2, true);
-          __syncwarp();
           process(r0, 3, true);
         }
         if (et == 0) ECB_STAMP(2 + g, 4 * use + 3);
@@ -408,33 +535,25 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       if (et == 0) ECB_STAMP(4, 8 * g + 6);
       // The row's two threads pool their bins: the k-th largest of the union of two
       // descending lists is  max_i min(mine[i-1], theirs[k-i-1])  (i taken from mine).  The
-      // partner's list travels through the (idle between the passes) score staging area of
-      // shared memory, 16 values per round; trev[i] = theirs[k-i-1].
-      const float* other_s = &T->stage_s[0][(g ^ 1) * NUM_EPI + et];
+      // partner's list travels through the (still empty) survivor area of shared memory.
+      float* exch = reinterpret_cast<float*>(surv);  // [NBINS][256]
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-      if (lane == 0) T->xmax_w[(g * NUM_EPI + et) >> 5] = xmax;  // read after the first bar.sync below
-      float trev[KMAX];
+      if (lane == 0) T->xmax_w[me >> 5] = xmax;  // read after the bar.sync below
 #pragma unroll
-      for (int i = 0; i < KMAX; ++i) trev[i] = -CUDART_INF_F;  // theirs[>= NBINS] does not exist
-#pragma unroll
-      for (int r = 0; r < NBINS / 16; ++r) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) stage_s[u * LS] = bin[r * 16 + u];
-        asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
-#pragma unroll
-        for (int i = 0; i < KMAX; ++i) {
-          const int t = k - i - 1 - r * 16;
-          if (t >= 0 && t < 16) trev[i] = other_s[t * LS];
-        }
-        asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
-      }
+      for (int u = 0; u < NBINS; ++u) exch[u * LS + me] = bin[u];
+      asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
+      const float* other = exch + ((g ^ 1) * NUM_EPI + et);
       float tau = -CUDART_INF_F;
 #pragma unroll
       for (int i = 0; i <= KMAX; ++i) {
-        const float mine = i == 0 ? CUDART_INF_F : (i - 1 < NBINS ? bin[i - 1 < NBINS ? i - 1 : 0] : -CUDART_INF_F);
-        const float t = i >= k ? CUDART_INF_F : trev[i < KMAX ? i : 0];
-        if (i <= k) tau = fmaxf(tau, fminf(mine, t));
+        // i entries from mine, k - i from theirs
+        if (i <= k) {
+          const float mine = i == 0 ? CUDART_INF_F : (i - 1 < NBINS ? bin[i - 1 < NBINS ? i - 1 : 0] : -CUDART_INF_F);
+          const int t = k - i - 1;   // index of the (k-i)-th of theirs
+          const float theirs = t < 0 ? CUDART_INF_F : (t < NBINS ? other[(t < NBINS ? t : 0) * LS] : -CUDART_INF_F);
+          tau = fmaxf(tau, fminf(mine, theirs));
+        }
       }
       // Pass A scored with the hi.hi product only: |score_A - score_B| <= 2^-11 (|hi_i||x_j| +
       // |x_i||hi_j|) <= 1.1 * 2^-10 |x_i| max_j|x_j|.  Lowering the bound by that margin keeps
@@ -442,67 +561,94 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       float cmax = 0.f;
 #pragma unroll
       for (int w = 0; w < 2 * NUM_EPI / 32; ++w) cmax = fmaxf(cmax, T->xmax_w[w]);
-      const float xi = valid ? xx[cloud_row0 + row] : 0.f;
       const float margin = 1.1f * 0.0009765625f * sqrtf(xi * cmax) + 1e-30f;
-      thr = fmaxf(tau - margin, -3.0e38f);  // masked candidates score -inf and must never pass
+      // masked candidates score -inf and must never pass; rows past the end keep nothing
+      thr = valid ? fmaxf(tau - margin, -3.0e38f) : CUDART_INF_F;
+      asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");  // bins read: the area may take survivors
       if (et == 0) ECB_STAMP(4, 8 * g + 7);
       run_tiles(std::integral_constant<int, 1>{});
-    }
-    if (!DEBUG) {
-      // Exact top-k of the row's survivors (both groups): rank = number of strictly better
-      // keys = output slot.  Once both groups have passed their last t_full wait every MMA
-      // has completed and the operand tiles are dead, so the survivor lists move from the
-      // L2-resident workspace into conflict-free columns of that shared memory.
-      asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
-      if (et == 0) ECB_STAMP(4, 8 * g + 2);
-      const int me = g * NUM_EPI + et, other = (g ^ 1) * NUM_EPI + et;
-      uint64_t* cols = reinterpret_cast<uint64_t*>(base);  // [cap][2*NUM_EPI] keys
       if (!valid) cnt = 0;
-      for (int e0 = 0; e0 < cnt; e0 += 8) {  // loads first, then stores: one L2 round trip per 8
-        uint64_t tmp[8];
+      // Top-k of the row's survivors (both groups), nearest first: rank = number of better
+      // entries = output slot.  Fast path: every thread ranks its OWN entries against the union
+      // by SCORE only (one compare on the ALU pipe + one add on the FMA pipe per pair).  Without
+      // equal scores the ranks of a row are a permutation, i.e. they sum to total*(total-1)/2;
+      // the two threads of a row compare that sum and, only if it falls short (equal scores:
+      // duplicate points, lattices), redo the row exactly under the total order (score, then
+      // smaller j).  Slots are staged in the (dead) operand ring and written out coalesced.
+      T->cnt_x[g][et] = cnt;
+      asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");  // both lists complete; every MMA done
+      if (et == 0) ECB_STAMP(4, 8 * g + 3);
+      int32_t* out_s = reinterpret_cast<int32_t*>(b_st);      // [128 rows][k]
+      const int cnt0 = T->cnt_x[0][et], cnt1 = T->cnt_x[1][et];
+      const int total = cnt0 + cnt1;
+      const uint64_t* col0 = surv + et;
+      const uint64_t* col1 = surv + NUM_EPI + et;
+      int32_t* orow = out_s + (q * 32 + lane) * k;
+      if (tl && blockIdx.x == 0 && blockIdx.y == 0 && g == 0) tl[5 * 256 + 128 + et] = ((long long)cnt0 << 32) | (unsigned)cnt1;
+      // the row's two threads split the union of both lists evenly (balanced work whatever the
+      // individual list lengths): mine is [lo, hi) of list 0 followed by list 1
+      const int half = (total + 1) >> 1;
+      const int lo = g * half, hi = min(total, lo + half);
+      auto entry = [&](int f) -> const uint64_t* { return f < cnt0 ? col0 + f * LS : col1 + (f - cnt0) * LS; };
+      int ranksum = 0;
+      for (int e0 = lo; e0 < hi; e0 += 8) {  // 8 entries in registers per sweep of the union
+        float so[8], rf[8];
+        uint32_t jo[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) tmp[u] = e0 + u < cnt ? __ldcg(mybuf + (e0 + u) * LS) : 0ull;
+        for (int u = 0; u < 8; ++u) {
+          const uint64_t w = e0 + u < hi ? *entry(e0 + u) : 0ull;
+          so[u] = e0 + u < hi ? __uint_as_float((uint32_t)(w >> 32)) : CUDART_INF_F;
+          jo[u] = (uint32_t)w;
+          rf[u] = 0.f;
+        }
+#pragma unroll 4
+        for (int f = 0; f < total; ++f) {
+          const float sf = reinterpret_cast<const float*>(entry(f))[1];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) rf[u] += (sf > so[u]) ? 1.f : 0.f;
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (e0 + u < cnt) cols[(e0 + u) * (2 * NUM_EPI) + me] = ordered_key(tmp[u]);
+          if (e0 + u < hi) {
+            const int r = (int)rf[u];
+            ranksum += r;
+            if (r < k) orow[r] = (int32_t)min(jo[u], (uint32_t)(N - 1));
+          }
       }
-      T->cnt_x[g][et] = cnt;
+      T->sum_x[g][et] = ranksum;
+      if (et == 0) ECB_STAMP(5, 8 + 4 * g);
       asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
-      if (et == 0) ECB_STAMP(4, 8 * g + 3);
-      if (valid) {
-        // The row's two threads split the union of both survivor lists evenly; each ranks its
-        // share against the whole union (keys are distinct, so ranks are a permutation).
-        const int cnt0 = T->cnt_x[0][et], cnt1 = T->cnt_x[1][et];
-        const int total = cnt0 + cnt1;
-        const uint64_t* col0 = cols + et;            // group 0's column, then group 1's
-        const uint64_t* col1 = cols + NUM_EPI + et - (size_t)cnt0 * (2 * NUM_EPI);
-        auto key_at = [&](int f) -> uint64_t {
-          return (f < cnt0 ? col0 : col1)[(size_t)f * (2 * NUM_EPI)];
-        };
-        int32_t* out = idx + (size_t)(cloud_row0 + row) * k;
-        if (g == 0)
-          for (int p = total; p < k; ++p) out[p] = N - 1;  // only with NaN input
-        const int half = (total + 1) >> 1;
-        const int lo = g * half, hi = min(total, lo + half);
-        for (int e0 = lo; e0 < hi; e0 += 8) {  // 8 keys in registers per sweep of the union
-          uint64_t own[8];
-          int rank[8];
+      if (et == 0) ECB_STAMP(5, 9 + 4 * g);
+      if (valid && T->sum_x[0][et] + T->sum_x[1][et] != total * (total - 1) / 2) {
+        // equal scores in this row: exact ranks under the total order
+        for (int e0 = lo; e0 < hi; e0 += 4) {
+          uint64_t own[4];
+          int rank[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            own[u] = e0 + u < hi ? key_at(e0 + u) : ~0ull;
+          for (int u = 0; u < 4; ++u) {
+            own[u] = e0 + u < hi ? ordered_key(*entry(e0 + u)) : ~0ull;
             rank[u] = 0;
           }
-#pragma unroll 4
+#pragma unroll 1
           for (int f = 0; f < total; ++f) {
-            const uint64_t kf = key_at(f);
+            const uint64_t kf = ordered_key(*entry(f));
 #pragma unroll
-            for (int u = 0; u < 8; ++u) rank[u] += (kf > own[u]);
+            for (int u = 0; u < 4; ++u) rank[u] += (kf > own[u]);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (e0 + u < hi && rank[u] < k)
-              out[rank[u]] = (int32_t)min(key_index(own[u]), (uint32_t)(N - 1));
+          for (int u = 0; u < 4; ++u)
+            if (e0 + u < hi && rank[u] < k) orow[rank[u]] = (int32_t)min(key_index(own[u]), (uint32_t)(N - 1));
         }
+      }
+      if (valid && g == 0)
+        for (int p = total; p < k; ++p) orow[p] = N - 1;  // only with NaN input
+      asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
+      if (et == 0) ECB_STAMP(5, 10 + 4 * g);
+      {
+        // the CTA's rows are consecutive in idx: one contiguous, coalesced block of nrows*k words
+        const int nrows = min(BM, Na - rt * BM);
+        int32_t* dst = idx + (size_t)(cloud_row0 + rt * BM) * k;
+        for (int w = me; w < nrows * k; w += 2 * NUM_EPI) dst[w] = out_s[w];
       }
       if (et == 0) ECB_STAMP(4, 8 * g + 4);
     }
@@ -511,6 +657,8 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  // no CTA of a cluster may exit while a peer can still signal its barriers
+  if (CL > 1) cluster_sync_all();
   if (tl && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -573,8 +721,8 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [rows, C] fp32 row-major, box = 32 channels x 128 rows, 128-byte swizzle, zero fill past the end
-int make_point_map(CUtensorMap* m, const float* p, long long rows, int C) {
+// [rows, C] fp32 row-major, box = 32 channels x box_rows rows, 128-byte swizzle, zero fill past the end
+int make_point_map(CUtensorMap* m, const float* p, long long rows, int C, int box_rows) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
     ecb200::set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -582,7 +730,7 @@ int make_point_map(CUtensorMap* m, const float* p, long long rows, int C) {
   }
   const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)C * sizeof(float)};
-  const cuuint32_t box[2] = {KB, BM};
+  const cuuint32_t box[2] = {KB, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -598,29 +746,83 @@ int make_point_map(CUtensorMap* m, const float* p, long long rows, int C) {
 struct OperandMaps {
   CUtensorMap hi, lo;
 };
-int make_operand(OperandMaps* m, const float* hi, const float* lo, long long rows, int C) {
-  int rc = make_point_map(&m->hi, hi, rows, C);
+int make_operand(OperandMaps* m, const float* hi, const float* lo, long long rows, int C, int box_rows) {
+  int rc = make_point_map(&m->hi, hi, rows, C, box_rows);
   if (rc) return rc;
-  return make_point_map(&m->lo, lo, rows, C);
+  return make_point_map(&m->lo, lo, rows, C, box_rows);
 }
 
+struct TcArgs {
+  const float *a_hi, *a_lo, *b_hi, *b_lo, *xx;
+  long long b_rows;   // rows of the B arrays
+  int clouds, C, Na, Nb, k;
+  int32_t* idx;
+  float* dbg;
+  long long* tl;
+};
+
 // clouds = grid.y; per cloud Na rows of A (queries / points) and Nb rows of B (candidates / Wcat rows)
-template <int NBINS, bool DEBUG>
-int launch_tc(const float* a_hi, const float* a_lo, const OperandMaps& Bm, const float* xx, int clouds, int C, int Na,
-              int Nb, int k, uint64_t* ws, int cap, int32_t* idx, float* dbg, cudaStream_t st,
-              long long* tl = nullptr) {
-  const int nkb = C / KB;
-  auto kern = knn_tc_kernel<NBINS, DEBUG>;
+template <bool DEBUG, int CL, int S, int CAP>
+int launch_tc(const TcArgs& a, cudaStream_t st) {
+  OperandMaps Bm;
+  int rc = make_operand(&Bm, a.b_hi, a.b_lo, a.b_rows, a.C, BM / CL);
+  if (rc) return rc;
+  const int nkb = a.C / KB;
+  auto kern = knn_tc_kernel<32, DEBUG, CL, S>;
+  constexpr size_t smem = smem_bytes(S, DEBUG ? 0 : CAP);
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static thread_local bool seen[ecb200::kMaxDevices] = {};
   if (ecb200::first_use_on_device(seen))
-    ECB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem_bytes()));
-  dim3 grid(ecb200::ceil_div(Na, BM), clouds);
-  // workspace = survivor keys [tiles][cap][2][128]
-  kern<<<grid, NT, smem_bytes(), st>>>(a_hi, a_lo, Bm.hi, Bm.lo, xx, Na, Nb, nkb, k, ws, cap, idx,
-                                          dbg, tl);
-  ECB_LAUNCH_CHECK("knn_tc_kernel");
+    ECB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ecb200::ceil_div(a.Na, BM), a.clouds);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a.a_hi, a.a_lo, Bm.hi, Bm.lo, a.xx, a.Na, a.Nb, nkb, a.k, CAP,
+                                     a.idx, a.dbg, a.tl);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    ecb200::set_error("launch of knn_tc_kernel failed: %s", cudaGetErrorString(e));
+    return ECB200_ERR_CUDA;
+  }
   return ECB200_OK;
+}
+
+// CTAs per cluster for a cloud of `tiles` row tiles: the largest of {4, 2, 1} that divides the
+// tile count and does not exceed the request (ECB200_KNN_CLUSTER, default 2; a tuning knob read once)
+int cluster_size(int tiles) {
+  static int want = -1;
+  if (want < 0) {
+    const char* e = getenv("ECB200_KNN_CLUSTER");
+    want = e ? atoi(e) : 2;
+    if (want < 1) want = 1;
+  }
+  if (want >= 4 && tiles % 4 == 0) return 4;
+  if (want >= 2 && tiles % 2 == 0) return 2;
+  return 1;
+}
+
+// survivor slots per thread (two threads per row): k + GUARD, the overflow check runs every GUARD
+// candidate columns (expected use ~12 at k = 20, ~30 at k = 40); ring depth from what is left of the
+// 227 KB: k <= 20 -> 4 stages + 36 slots (204 KB), k <= 40 -> 3 stages + 56 slots (212 KB)
+int launch_knn(const TcArgs& a, cudaStream_t st) {
+  const int cl = cluster_size(ecb200::ceil_div(a.Na, BM));
+  if (a.k <= 20) {
+    if (cl == 4) return launch_tc<false, 4, 4, 20 + GUARD>(a, st);
+    if (cl == 2) return launch_tc<false, 2, 4, 20 + GUARD>(a, st);
+    return launch_tc<false, 1, 4, 20 + GUARD>(a, st);
+  }
+  if (cl == 4) return launch_tc<false, 4, 3, KMAX + GUARD>(a, st);
+  if (cl == 2) return launch_tc<false, 2, 3, KMAX + GUARD>(a, st);
+  return launch_tc<false, 1, 3, KMAX + GUARD>(a, st);
 }
 
 __global__ void split_rows_tf32_kernel(const float* __restrict__ src, long long n, float* __restrict__ hi,
@@ -645,35 +847,26 @@ extern "C" int ecb200_split_tf32(const float* x, int B, int C, int N, float* hi,
   return ECB200_OK;
 }
 
-// survivor slots per (row, epilogue group) in the workspace (2 x 32 pooled bins per row:
-// expected use ~12 per thread at k = 20, ~32 at k = 40; overflow falls back to an exact
-// in-place shrink before a 32-column chunk, so cap >= k + 32).  cap * 256 threads * 8 bytes must fit the >= 160 KB of operand tiles that the
-// final ranking reuses.
-static int survivor_cap(int k) { return k <= 20 ? 56 : 80; }
-
+// The survivor lists live in shared memory; no global workspace is needed any more.  The entry
+// point keeps its (workspace, bytes) arguments for ABI stability: any non-null pointer will do.
 extern "C" size_t ecb200_knn_tc_workspace_bytes(int B, int N, int k) {
-  const size_t tiles = (size_t)B * ecb200::ceil_div(N, BM);
-  return tiles * 2 * NUM_EPI * (size_t)survivor_cap(k) * sizeof(uint64_t);
+  (void)B; (void)N; (void)k;
+  return 256;
 }
 
 extern "C" int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, int B, int C, int N,
                              int k, int sorted, int32_t* idx, void* workspace, size_t workspace_bytes,
                              void* stream) {
   (void)sorted;  // the rank-based final stage always yields nearest-first order
+  (void)workspace_bytes;
   ECB_REQUIRE(hi && lo && xx && idx && workspace, "ecb200_knn_tc: null pointer");
   ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1, "ecb200_knn_tc: bad shape B=%d N=%d", B, N);
   ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB,
               "ecb200_knn_tc: C=%d must be a multiple of 32 in [32, 128]", C);
   ECB_REQUIRE(k >= 1 && k <= N, "ecb200_knn_tc: k=%d out of range for N=%d (selected index k out of range)", k, N);
   ECB_REQUIRE(k <= KMAX, "ecb200_knn_tc: k=%d exceeds %d (use ecb200_knn)", k, KMAX);
-  ECB_REQUIRE(workspace_bytes >= ecb200_knn_tc_workspace_bytes(B, N, k),
-              "ecb200_knn_tc: workspace too small (%zu < %zu bytes)", workspace_bytes,
-              ecb200_knn_tc_workspace_bytes(B, N, k));
-  OperandMaps X;
-  int rc = make_operand(&X, hi, lo, (long long)B * N, C);
-  if (rc) return rc;
-  return launch_tc<32, false>(hi, lo, X, xx, B, C, N, N, k, (uint64_t*)workspace, survivor_cap(k), idx, nullptr,
-                              (cudaStream_t)stream);
+  TcArgs a = {hi, lo, hi, lo, xx, (long long)B * N, B, C, N, N, k, idx, nullptr, nullptr};
+  return launch_knn(a, (cudaStream_t)stream);
 }
 
 extern "C" int ecb200_debug_tc_timeline(const float* hi, const float* lo, const float* xx, int B, int C,
@@ -681,11 +874,8 @@ extern "C" int ecb200_debug_tc_timeline(const float* hi, const float* lo, const 
                                         long long* timeline, void* stream) {
   ECB_REQUIRE(hi && lo && xx && idx && workspace && timeline, "ecb200_debug_tc_timeline: null pointer");
   ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB && k <= KMAX && k <= N, "bad shape");
-  OperandMaps X;
-  int rc = make_operand(&X, hi, lo, (long long)B * N, C);
-  if (rc) return rc;
-  return launch_tc<32, false>(hi, lo, X, xx, B, C, N, N, k, (uint64_t*)workspace, survivor_cap(k), idx, nullptr,
-                              (cudaStream_t)stream, timeline);
+  TcArgs a = {hi, lo, hi, lo, xx, (long long)B * N, B, C, N, N, k, idx, nullptr, timeline};
+  return launch_knn(a, (cudaStream_t)stream);
 }
 
 extern "C" int ecb200_debug_tc_scores(const float* hi, const float* lo, const float* xx, int B, int C,
@@ -694,10 +884,8 @@ extern "C" int ecb200_debug_tc_scores(const float* hi, const float* lo, const fl
   ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1, "ecb200_debug_tc_scores: bad shape");
   ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB,
               "ecb200_debug_tc_scores: C=%d must be a multiple of 32 in [32, 128]", C);
-  OperandMaps X;
-  int rc = make_operand(&X, hi, lo, (long long)B * N, C);
-  if (rc) return rc;
-  return launch_tc<32, true>(hi, lo, X, xx, B, C, N, N, 1, nullptr, 0, nullptr, scores, (cudaStream_t)stream);
+  TcArgs a = {hi, lo, hi, lo, xx, (long long)B * N, B, C, N, N, 1, nullptr, scores, nullptr};
+  return launch_tc<true, 1, 5, 0>(a, (cudaStream_t)stream);
 }
 
 extern "C" int ecb200_split_rows_tf32(const float* src, long long n, float* hi, float* lo, void* stream) {
@@ -713,9 +901,7 @@ extern "C" int ecb200_point_gemm_tc(const float* xhi, const float* xlo, const fl
   ECB_REQUIRE(M >= 1 && M < (1LL << 31) && Co2 >= 1, "ecb200_point_gemm_tc: bad shape");
   ECB_REQUIRE(C % KB == 0 && C >= KB && C <= KB * MAX_KB,
               "ecb200_point_gemm_tc: C=%d must be a multiple of 32 in [32, 128]", C);
-  OperandMaps W;
-  int rc = make_operand(&W, whi, wlo, Co2, C);
-  if (rc) return rc;
   // one "cloud": A = all M points, B = the 2Co rows of Wcat, dense store of the tiles into Y[M, 2Co]
-  return launch_tc<32, true>(xhi, xlo, W, nullptr, 1, C, (int)M, Co2, 1, nullptr, 0, nullptr, Y, (cudaStream_t)stream);
+  TcArgs a = {xhi, xlo, whi, wlo, nullptr, (long long)Co2, 1, C, (int)M, Co2, 1, nullptr, Y, nullptr};
+  return launch_tc<true, 1, 5, 0>(a, (cudaStream_t)stream);
 }

@@ -13,6 +13,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp (the same lane every time).  Code that issues tcgen05.mma /
+// TMA keeps the WHOLE warp in the loop and elects the issuer per instruction group: the operands
+// then stay warp-uniform (uniform registers), where an `if (lane == 0)` region makes the compiler
+// wrap every UTCHMMA / UTMALDG in an R2UR + ELECT "waterfall" of ~15 instructions.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

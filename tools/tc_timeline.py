@@ -35,9 +35,15 @@ for g in (0, 1):
     print(f"epilogue group {g}: per use (begin, hx-barrier done, t_full acquired, done)")
     for u in range(nct):
         print("   use", u, [rel(v) for v in t[2 + g, 4 * u:4 * u + 4]])
-    print("   pass ends / pre-copy / post-copy / ranked:", [rel(v) for v in t[4, 8 * g:8 * g + 5]])
+    print("   pass A end / pass B end / - / keys converted / ranked:", [rel(v) for v in t[4, 8 * g:8 * g + 5]])
     print("   tau stage: start / sorted / done:", [rel(v) for v in t[4, 8 * g + 5:8 * g + 8]])
+    print("   rank stage: fast ranks done / barrier / slow path + barrier:", [rel(v) for v in t[5, 8 + 4 * g:11 + 4 * g]])
 
+sv = t[5, 128:256]
+c0, c1 = (sv >> 32).float(), (sv & 0xffffffff).float()
+tot = c0 + c1
+print(f"survivors per row (CTA 0,0): mean {tot.mean():.1f} max {tot.max():.0f}; per thread mean {c0.mean():.1f}/{c1.mean():.1f} max {c0.max():.0f}/{c1.max():.0f}; "
+      f"per-warp max of total: {[int(tot[w*32:(w+1)*32].max()) for w in range(4)]}")
 # every CTA: start / duration (us) relative to the first start, by SM
 st0 = int(allc[:, 0].min())
 dur = (allc[:, 1] - allc[:, 0]).double() / 1e3
