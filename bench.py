@@ -552,7 +552,7 @@ def run_b200(a):
     # layer (norm terms and the error-compensation MMAs do not count)
     roof = None
     knn_flops = sum(2.0 * M * N * c for c, _ in layers if c % 32 == 0 and 32 <= c <= 128)
-    t_us = kernel_us("knn_tc_kernel<32, 0>") or kernel_us("knn_tc_kernel<32, false>")
+    t_us = kernel_us("knn_tc_kernel<32, false") or kernel_us("knn_tc_kernel<32, 0")
     src = "in-graph (CUPTI)"
     if not t_us and entry_ms("ecb200_knn_tc"):
         t_us, src = entry_ms("ecb200_knn_tc") * 1e3, "eager CUDA-event brackets"

@@ -536,22 +536,28 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       // The row's two threads pool their bins: the k-th largest of the union of two
       // descending lists is  max_i min(mine[i-1], theirs[k-i-1])  (i taken from mine).  The
       // partner's list travels through the (still empty) survivor area of shared memory.
-      float* exch = reinterpret_cast<float*>(surv);  // [NBINS][256]
+      // exchange area [k][256] in the (still empty) survivor area, written REVERSED: slot i holds
+      // the (k-i)-th largest bin, so the reader walks it with static offsets
+      float* exch = reinterpret_cast<float*>(surv);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
       if (lane == 0) T->xmax_w[me >> 5] = xmax;  // read after the bar.sync below
+      {
+        float* wr = exch + (size_t)(k - 1) * LS + me;     // slot k-1-u  <-  bin[u]
 #pragma unroll
-      for (int u = 0; u < NBINS; ++u) exch[u * LS + me] = bin[u];
+        for (int u = 0; u < NBINS; ++u)
+          if (u < k) wr[-u * LS] = bin[u];
+        for (int i = 0; i < k - NBINS; ++i) exch[i * LS + me] = -CUDART_INF_F;   // k > 32: ranks that do not exist
+      }
       asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
       const float* other = exch + ((g ^ 1) * NUM_EPI + et);
       float tau = -CUDART_INF_F;
 #pragma unroll
       for (int i = 0; i <= KMAX; ++i) {
-        // i entries from mine, k - i from theirs
+        // i entries from mine, k - i from theirs: min(mine[i-1], theirs[k-i-1])
         if (i <= k) {
           const float mine = i == 0 ? CUDART_INF_F : (i - 1 < NBINS ? bin[i - 1 < NBINS ? i - 1 : 0] : -CUDART_INF_F);
-          const int t = k - i - 1;   // index of the (k-i)-th of theirs
-          const float theirs = t < 0 ? CUDART_INF_F : (t < NBINS ? other[(t < NBINS ? t : 0) * LS] : -CUDART_INF_F);
+          const float theirs = i == k ? CUDART_INF_F : other[(i < KMAX ? i : 0) * LS];
           tau = fmaxf(tau, fminf(mine, theirs));
         }
       }
@@ -568,6 +574,16 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       if (et == 0) ECB_STAMP(4, 8 * g + 7);
       run_tiles(std::integral_constant<int, 1>{});
       if (!valid) cnt = 0;
+      {
+        // the union of a row's two lists is ranked in the (then dead) operand ring, one KB per slot:
+        // a list longer than half of the ring's slots is cut to its own best k first (exact: at
+        // most k entries of a list can make the row's top k).  Never taken with the 4-stage ring.
+        constexpr int UNI_HALF = S * STAGE_BYTES / 1024 / 2;
+        if (cnt > UNI_HALF) {
+          shrink_survivors(sv, cnt, k);
+          cnt = k;
+        }
+      }
       // Top-k of the row's survivors (both groups), nearest first: rank = number of better
       // entries = output slot.  Fast path: every thread ranks its OWN entries against the union
       // by SCORE only (one compare on the ALU pipe + one add on the FMA pipe per pair).  Without
@@ -578,37 +594,63 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       T->cnt_x[g][et] = cnt;
       asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");  // both lists complete; every MMA done
       if (et == 0) ECB_STAMP(4, 8 * g + 3);
-      int32_t* out_s = reinterpret_cast<int32_t*>(b_st);      // [128 rows][k]
+      // the operand ring is dead now (every MMA has completed): it takes the row's UNION of both
+      // lists, slot-major [slot][128 rows] (conflict-free, and a plain strided walk for the
+      // ranking loop); at most 2k slots = 2k KB <= the ring's 96 KB
+      uint64_t* uni = reinterpret_cast<uint64_t*>(b_st) + et;           // slot f of this row at uni[f * NUM_EPI]
       const int cnt0 = T->cnt_x[0][et], cnt1 = T->cnt_x[1][et];
       const int total = cnt0 + cnt1;
-      const uint64_t* col0 = surv + et;
-      const uint64_t* col1 = surv + NUM_EPI + et;
+      // staged output [128 rows][k]: in the survivor area, which is dead once the lists have moved
+      int32_t* out_s = reinterpret_cast<int32_t*>(surv);
       int32_t* orow = out_s + (q * 32 + lane) * k;
+      {
+        uint64_t* dstc = uni + (size_t)(g == 0 ? 0 : cnt0) * NUM_EPI;
+        for (int e0 = 0; e0 < cnt; e0 += 8) {   // loads first, then stores: one shared-memory round trip per 8
+          uint64_t w[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) w[u] = e0 + u < cnt ? sv[(e0 + u) * LS] : 0ull;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (e0 + u < cnt) dstc[(e0 + u) * NUM_EPI] = w[u];
+        }
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");
+      if (et == 0) ECB_STAMP(4, 8 * g + 2);
       if (tl && blockIdx.x == 0 && blockIdx.y == 0 && g == 0) tl[5 * 256 + 128 + et] = ((long long)cnt0 << 32) | (unsigned)cnt1;
-      // the row's two threads split the union of both lists evenly (balanced work whatever the
-      // individual list lengths): mine is [lo, hi) of list 0 followed by list 1
+      // the row's two threads split the union evenly (balanced work whatever the individual list
+      // lengths): mine is [lo, hi)
       const int half = (total + 1) >> 1;
       const int lo = g * half, hi = min(total, lo + half);
-      auto entry = [&](int f) -> const uint64_t* { return f < cnt0 ? col0 + f * LS : col1 + (f - cnt0) * LS; };
+      constexpr int CH = 9;   // own entries per sweep of the union: two sweeps cover total <= 36
       int ranksum = 0;
-      for (int e0 = lo; e0 < hi; e0 += 8) {  // 8 entries in registers per sweep of the union
-        float so[8], rf[8];
-        uint32_t jo[8];
+      for (int e0 = lo; e0 < hi; e0 += CH) {
+        float so[CH], rf[CH];
+        uint32_t jo[CH];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint64_t w = e0 + u < hi ? *entry(e0 + u) : 0ull;
+        for (int u = 0; u < CH; ++u) {
+          const uint64_t w = e0 + u < hi ? uni[(e0 + u) * NUM_EPI] : 0ull;
           so[u] = e0 + u < hi ? __uint_as_float((uint32_t)(w >> 32)) : CUDART_INF_F;
           jo[u] = (uint32_t)w;
           rf[u] = 0.f;
         }
+        const float* sc = reinterpret_cast<const float*>(uni) + 1;   // score word of slot f at sc[f * 2 * NUM_EPI]
 #pragma unroll 4
         for (int f = 0; f < total; ++f) {
-          const float sf = reinterpret_cast<const float*>(entry(f))[1];
+          const float sf = sc[f * 2 * NUM_EPI];
+          // compare on the ALU pipe (FSETP), predicated add on the FMA pipe; written out because the
+          // compiler's FSET.BF form measured ~4x slower here
 #pragma unroll
-          for (int u = 0; u < 8; ++u) rf[u] += (sf > so[u]) ? 1.f : 0.f;
+          for (int u = 0; u < CH; ++u)
+            asm("{\n\t"
+                ".reg .pred p;\n\t"
+                "setp.gt.f32 p, %1, %2;\n\t"
+                "@p add.f32 %0, %0, 0f3F800000;\n\t"
+                "}"
+                : "+f"(rf[u])
+                : "f"(sf), "f"(so[u]));
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < CH; ++u)
           if (e0 + u < hi) {
             const int r = (int)rf[u];
             ranksum += r;
@@ -626,12 +668,12 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
           int rank[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            own[u] = e0 + u < hi ? ordered_key(*entry(e0 + u)) : ~0ull;
+            own[u] = e0 + u < hi ? ordered_key(uni[(e0 + u) * NUM_EPI]) : ~0ull;
             rank[u] = 0;
           }
 #pragma unroll 1
           for (int f = 0; f < total; ++f) {
-            const uint64_t kf = ordered_key(*entry(f));
+            const uint64_t kf = ordered_key(uni[f * NUM_EPI]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) rank[u] += (kf > own[u]);
           }
@@ -797,12 +839,15 @@ int launch_tc(const TcArgs& a, cudaStream_t st) {
 }
 
 // CTAs per cluster for a cloud of `tiles` row tiles: the largest of {4, 2, 1} that divides the
-// tile count and does not exceed the request (ECB200_KNN_CLUSTER, default 2; a tuning knob read once)
+// tile count and does not exceed the request (ECB200_KNN_CLUSTER, a tuning knob read once).
+// Default 1: on B200 the candidate tiles are served from L2 at ~4 KB/clk chip-wide, below its limit,
+// and the lock-step of a cluster costs 3-7 % (measured at N = 1024: 58.2 / 60.5 / 62.3 us for 1 / 2 / 4);
+// multicast pays only when many more row tiles share a cloud than the L2 can feed.
 int cluster_size(int tiles) {
   static int want = -1;
   if (want < 0) {
     const char* e = getenv("ECB200_KNN_CLUSTER");
-    want = e ? atoi(e) : 2;
+    want = e ? atoi(e) : 1;
     if (want < 1) want = 1;
   }
   if (want >= 4 && tiles % 4 == 0) return 4;

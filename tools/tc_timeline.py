@@ -7,9 +7,30 @@ import torch
 import dgcnn_pytorch_b200 as ec
 import edgeconv_oracle as orc
 L = ec._lib
-B, C, N, k = (int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "32,64,1024,20".split(",")))
 dev = torch.device("cuda:0")
-x = orc.synthetic_features(B, C, N, seed=1).to(dev)
+if len(sys.argv) > 1 and sys.argv[1].startswith("model"):
+    # the input of EdgeConv layer `layer` (2..4) of a DGCNN-cls forward on synthetic clouds: real activations
+    from types import SimpleNamespace
+    layer = int(sys.argv[1].split(":")[1])
+    B, N, k = 32, 1024, 20
+    torch.manual_seed(1)
+    net = ec.DGCNN_cls(SimpleNamespace(emb_dims=1024, k=k, dropout=0.5)).to(dev).train()
+    seen = []
+    orig = ec.ops.split_tf32_op
+    def spy(x):
+        seen.append(x.detach().clone())
+        return orig(x)
+    ec.ops.split_tf32_op = spy
+    import dgcnn_pytorch_b200.dgcnn as dg
+    dg.ops.split_tf32_op = spy
+    with torch.no_grad():
+        net(orc.synthetic_xyz(B, N, seed=100).to(dev))
+    x = seen[layer - 2].contiguous()
+    C = x.shape[1]
+    print(f"layer {layer} input: C={C}, mean {x.mean():.3f} std {x.std():.3f}")
+else:
+    B, C, N, k = (int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "32,64,1024,20".split(",")))
+    x = orc.synthetic_features(B, C, N, seed=1).to(dev)
 hi = torch.empty(B * N, C, device=dev); lo = torch.empty_like(hi); xx = torch.empty(B * N, device=dev)
 idx = torch.empty(B, N, k, device=dev, dtype=torch.int32)
 nb = L.load().ecb200_knn_tc_workspace_bytes(B, N, k)
@@ -35,7 +56,7 @@ for g in (0, 1):
     print(f"epilogue group {g}: per use (begin, hx-barrier done, t_full acquired, done)")
     for u in range(nct):
         print("   use", u, [rel(v) for v in t[2 + g, 4 * u:4 * u + 4]])
-    print("   pass A end / pass B end / - / keys converted / ranked:", [rel(v) for v in t[4, 8 * g:8 * g + 5]])
+    print("   pass A end / pass B end / union copied / lists complete / ranked:", [rel(v) for v in t[4, 8 * g:8 * g + 5]])
     print("   tau stage: start / sorted / done:", [rel(v) for v in t[4, 8 * g + 5:8 * g + 8]])
     print("   rank stage: fast ranks done / barrier / slow path + barrier:", [rel(v) for v in t[5, 8 + 4 * g:11 + 4 * g]])
 
@@ -54,3 +75,30 @@ first = beg < 1.0
 print(f"  first wave: {int(first.sum())} CTAs, duration median {dur[first].median():.1f} max {dur[first].max():.1f}; "
       f"later CTAs: start median {beg[~first].median() if (~first).any() else 0:.1f} duration median "
       f"{dur[~first].median() if (~first).any() else 0:.1f} max {dur[~first].max() if (~first).any() else 0:.1f}")
+
+# warm, back-to-back launches timed with CUDA events (sustained clocks), and the SM clock implied by
+# CTA (0,0): cycles between its first and last stamp vs its wall-clock duration
+for _ in range(5):
+    L.call("ecb200_knn_tc", P(hi), P(lo), P(xx), B, C, N, k, 1, P(idx), P(ws), nb, st)
+torch.cuda.synchronize()
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s.record()
+for _ in range(50):
+    L.call("ecb200_knn_tc", P(hi), P(lo), P(xx), B, C, N, k, 1, P(idx), P(ws), nb, st)
+e.record()
+torch.cuda.synchronize()
+us = s.elapsed_time(e) * 1e3 / 50
+print(f"50 back-to-back launches: {us:.1f} us each = {2.0 * B * N * N * C / us / 1e6:.1f} TFLOP/s "
+      f"({2.0 * B * N * N * C / us / 1e6 / 268.2:.3f} of the 3xTF32 roofline 268.2)")
+import numpy as np
+d = dur.numpy(); bg = beg.numpy(); sm = allc[:, 2].numpy()
+nrt = (N + 127) // 128
+print("CTA duration percentiles (us) 10/50/90/99/max:", [round(float(np.percentile(d, p)), 1) for p in (10, 50, 90, 99, 100)])
+print("  by row tile (blockIdx.x):", [round(float(d[i::nrt].mean()), 1) for i in range(nrt)])
+order = np.argsort(-d)[:12]
+print("  slowest CTAs (tile, cloud, sm, start, dur):", [(int(i % nrt), int(i // nrt), int(sm[i]), round(float(bg[i]), 1), round(float(d[i]), 1)) for i in order])
+per_sm = {}
+for i in range(len(d)):
+    per_sm.setdefault(int(sm[i]), []).append((float(bg[i]), float(d[i])))
+busy = sorted(((sum(x[1] for x in v), len(v), s) for s, v in per_sm.items()), reverse=True)
+print("  busiest SMs (sum of CTA durations, #CTAs, sm):", [(round(b, 1), n, s) for b, n, s in busy[:8]], " least:", [(round(b, 1), n, s) for b, n, s in busy[-4:]])
