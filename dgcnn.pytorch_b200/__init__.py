@@ -5,9 +5,10 @@ dotted name); import it through the ``dgcnn_pytorch_b200`` shim at the repo
 root:  ``import dgcnn_pytorch_b200 as ec``.
 """
 from . import _lib, ops
-from .dgcnn import DGCNN, edgeconv_block, get_graph_feature, knn
-from .model import ClsHead, DGCNN_cls, cal_loss
+from .dgcnn import DGCNN, edgeconv_block, get_graph_feature, knn, two_conv_edge_block
+from .model import ClsHead, DGCNN_cls, DGCNN_semseg, IOStream, PointNet, cal_loss
 from .ops import edgeconv
 from .runtime import GraphedTrainStep
 
-__all__ = ["DGCNN", "GraphedTrainStep", "DGCNN_cls", "ClsHead", "cal_loss", "edgeconv", "edgeconv_block", "get_graph_feature", "knn", "ops", "_lib"]
+__all__ = ["DGCNN", "GraphedTrainStep", "DGCNN_cls", "DGCNN_semseg", "PointNet", "ClsHead", "IOStream", "cal_loss",
+           "edgeconv", "edgeconv_block", "two_conv_edge_block", "get_graph_feature", "knn", "ops", "_lib"]

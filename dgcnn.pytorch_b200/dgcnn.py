@@ -21,7 +21,7 @@ def knn(x: torch.Tensor, k: int) -> torch.Tensor:
     """models/dgcnn.py:6-12.  x [B,C,N] -> int64 [B,N,k]: indices of the k nearest
     points (self included) by the reference's -|xi|^2 + 2 xi.xj - |xj|^2 score,
     nearest first; equal scores resolve to the smaller index."""
-    return ops.knn_op(_as_f32(x), int(k)).long()
+    return ops.knn_cached(_as_f32(x), int(k)).long()
 
 
 def _as_f32(x: torch.Tensor) -> torch.Tensor:
@@ -48,7 +48,7 @@ def get_graph_feature(x: torch.Tensor, k: int = 20, knn_only: bool = False,
     x = _as_f32(x)
     if idx is None:
         src = x[:, 6:] if dim9 else x
-        idx32 = ops.knn_op(src.contiguous(), int(k))
+        idx32 = ops.knn_cached(src.contiguous(), int(k))
     else:
         idx32 = ops.check_neighbour_indices(idx, x.shape[0], x.shape[2])
     if knn_only:
@@ -102,13 +102,42 @@ def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
         if idx is None:
             idx = ops.knn_tc_op(xhi, xlo, xx, B, N, int(k))
     if idx is None:
-        idx = ops.knn_op(x.detach().contiguous(), int(k), False)   # order over k is irrelevant here
+        idx = ops.knn_cached(x.detach().contiguous(), int(k), False)   # order over k is irrelevant here
     group = _sync_group(bn)
     slope = float(getattr(act, "negative_slope", 0.0))
     out = ops.edgeconv(x, idx, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                        bn.num_batches_tracked, bn.training, bn.momentum, bn.eps, slope,
                        subtract_center, group, xhi, xlo, return_point_major)
     return out, idx
+
+
+def two_conv_edge_block(x: torch.Tensor, block1: nn.Sequential, block2: nn.Sequential, k: int,
+                        idx: Optional[torch.Tensor] = None, subtract_center: bool = False,
+                        dim9: bool = False) -> torch.Tensor:
+    """``block2(block1(get_graph_feature(x, k))).max(-1)[0]``: the two-conv edge block of the
+    reference's PositionEmbedding (models/layers.py:45-52) and of upstream's part-seg / sem-seg
+    EdgeConv blocks.  x [B,C,N] -> [B,Co2,N].
+
+    In inference (no gradient required) the block runs FUSED: the first conv splits as
+    W1.[x_j ; x_i] = U_j + V_i (one per-point GEMM), and one kernel gathers U rows, applies BN1 +
+    LeakyReLU in registers, multiplies the 128-edge tile with W2 on the tensor cores (3xTF32,
+    accumulators in tensor memory) and reduces max / min over k with the BN2 statistics in its
+    epilogue (ops.two_conv_block) -- neither [B,2C,N,k] nor [B,Co1,N,k] ever exists.  When a
+    gradient is required the block runs on the materialising path below (graph-feature kernel +
+    the library convolutions under autograd), which is the reference's own arithmetic."""
+    x = _as_f32(x)
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(
+        p.requires_grad for blk in (block1, block2) for p in blk.parameters()))
+    if not need_grad and ops.two_conv_block_supported(x.shape[1], block1, block2, int(k)):
+        src = x[:, 6:].contiguous() if dim9 else x
+        if idx is None:
+            idx32 = ops.knn_op(src, int(k), False)
+        else:
+            idx32 = ops.check_neighbour_indices(idx, x.shape[0], x.shape[2])
+        return ops.two_conv_block(x, idx32, block1, block2, subtract_center,
+                                  _sync_group(block1[1]), _sync_group(block2[1]))
+    gf = get_graph_feature(x, k=k, idx=idx, dim9=dim9, subtract_center=subtract_center)
+    return block2(block1(gf)).max(dim=-1, keepdim=False)[0]
 
 
 class DGCNN(nn.Module):

@@ -613,6 +613,123 @@ def embed_pool(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor, running_m
     return res[0]
 
 
+# ---------------------------------------------------- two-conv edge block, fused forward (row f-1)
+def two_conv_block_supported(C: int, block1, block2, k: int) -> bool:
+    """Shapes ecb200_two_conv_fwd takes: bias-free 1x1 convs, C1 in {32,64}, C2 in {32,64,128}."""
+    import torch.nn as nn
+    try:
+        c1, bn1, c2, bn2 = block1[0], block1[1], block2[0], block2[1]
+    except (IndexError, TypeError):
+        return False
+    ok = (isinstance(c1, nn.Conv2d) and isinstance(c2, nn.Conv2d) and c1.bias is None and c2.bias is None
+          and tuple(c1.kernel_size) == (1, 1) and tuple(c2.kernel_size) == (1, 1)
+          and isinstance(bn1, nn.modules.batchnorm._BatchNorm) and isinstance(bn2, nn.modules.batchnorm._BatchNorm)
+          and bn1.affine and bn2.affine)
+    return bool(ok and c1.in_channels == 2 * C and c1.out_channels in (32, 64) and c2.in_channels == c1.out_channels
+                and c2.out_channels in (32, 64, 128) and 1 <= k <= MAX_K
+                and os.environ.get("ECB200_TWO_CONV", "fused") == "fused")
+
+
+def _bn_affine(bn, stats: Optional[Tensor], group: int, Co: int, dev) -> Tensor:
+    """[4, Co] = (mean, invstd, a, b) of a BatchNorm layer: from the batch statistics buffer (training
+    mode or no running statistics; all-reduced under SyncBatchNorm, running statistics updated) or
+    from the running statistics."""
+    use_batch = stats is not None
+    affine = torch.empty(4, Co, device=dev, dtype=torch.float32)
+    mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * Co * r) for r in range(4))
+    g32, b32 = bn.weight.detach().contiguous().float(), bn.bias.detach().contiguous().float()
+    st = c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    if use_batch and group:
+        _allreduce_stats(stats, group)
+    _lib.call("ecb200_bn_finalize", _ptr(stats), _ptr(g32), _ptr(b32),
+              None if use_batch else _ptr(bn.running_mean), None if use_batch else _ptr(bn.running_var),
+              int(use_batch), float(bn.eps), Co, mean, invstd, a, b, st)
+    if use_batch and bn.training and bn.running_mean is not None:
+        mom = -1.0 if bn.momentum is None else float(bn.momentum)
+        _lib.call("ecb200_bn_update_running", _ptr(stats), Co, mom, _ptr(bn.running_mean), _ptr(bn.running_var),
+                  _ptr(bn.num_batches_tracked), st)
+    return affine
+
+
+@torch.no_grad()
+def two_conv_block(x: Tensor, idx: Tensor, block1, block2, subtract_center: bool = False,
+                   group1: int = 0, group2: int = 0) -> Tensor:
+    """max_k LeakyReLU(BN2(W2 . LeakyReLU(BN1(W1 . [x_j (- x_i) ; x_i]))))  ->  [B, C2, N], fused
+    (csrc/two_conv.cu); forward only -- see dgcnn.two_conv_edge_block for the differentiable path."""
+    _check_cuda_f32("x", x, 3)
+    B, C, N = x.shape
+    k = idx.shape[-1]
+    conv1, bn1, act1 = block1[0], block1[1], block1[2]
+    conv2, bn2, act2 = block2[0], block2[1], block2[2]
+    C1, C2 = conv1.out_channels, conv2.out_channels
+    M = B * N
+    dev = x.device
+    x = x.contiguous()
+    idx = idx.contiguous()
+    f32 = dict(device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        st = _stream(x)
+        w1 = conv1.weight.detach().reshape(C1, 2 * C).contiguous().float()
+        Wcat = torch.empty(2 * C1, C, **f32)
+        Y = torch.empty(M, 2 * C1, **f32)
+        _lib.call("ecb200_pack_weight", _ptr(w1), C1, C, int(subtract_center), _ptr(Wcat), st)
+        _lib.call("ecb200_point_gemm", _ptr(x), _ptr(Wcat), B, C, N, 2 * C1, _ptr(Y), st)
+        batch1 = bool(bn1.training or bn1.running_mean is None)
+        stats1 = None
+        if batch1:
+            # BatchNorm1 statistics over all edges: the gather kernel of the single-conv path
+            stats1 = torch.zeros(2 * C1 + 1, device=dev, dtype=torch.float64)
+            g1 = bn1.weight.detach().contiguous().float()
+            sel1 = torch.empty(M, C1, **f32)
+            arg1 = torch.empty(M, C1, device=dev, dtype=torch.uint8)
+            _lib.call("ecb200_edge_gather", _ptr(Y), _ptr(idx), _ptr(g1), B, N, k, C1, _ptr(sel1), _ptr(arg1),
+                      None, _ptr(stats1), st)
+        aff1 = _bn_affine(bn1, stats1, group1, C1, dev)
+        w2 = conv2.weight.detach().reshape(C2, C1).contiguous().float()
+        w2s = torch.empty(2, C2, C1, **f32)
+        _lib.call("ecb200_split_rows_tf32", _ptr(w2), C2 * C1, _ptr(w2s[0]), _ptr(w2s[1]), st)
+        batch2 = bool(bn2.training or bn2.running_mean is None)
+        stats2 = torch.zeros(2 * C2 + 1, device=dev, dtype=torch.float64) if batch2 else None
+        sel2 = torch.empty(M, C2, **f32)
+        g2 = bn2.weight.detach().contiguous().float()
+        _lib.call("ecb200_two_conv_fwd", _ptr(Y), _ptr(idx), _ptr(aff1[2]), _ptr(aff1[3]),
+                  float(getattr(act1, "negative_slope", 0.0)), _ptr(w2s[0]), _ptr(w2s[1]), _ptr(g2),
+                  B, N, k, C1, C2, _ptr(sel2), _ptr(stats2), st)
+        aff2 = _bn_affine(bn2, stats2, group2, C2, dev)
+        out = torch.empty(B, C2, N, **f32)
+        _lib.call("ecb200_edge_apply", _ptr(sel2), _ptr(aff2[2]), _ptr(aff2[3]),
+                  float(getattr(act2, "negative_slope", 0.0)), B, N, C2, _ptr(out), None, C2, st)
+    return out
+
+
+# ------------------------------------------------------------- kNN result reuse (row f-3, part 1)
+# The reference's part-seg Net computes knn(src, k) on the SAME xyz tensor three times per forward
+# (models/dgcnn.py:84 via DGCNN.forward, models/model_partseg.py:26 in compute_hog_1x1, and
+# models/layers.py:45 via PositionEmbedding).  One entry per device: the last xyz-sized query and
+# its graph.  The key holds the tensor's storage (so its address cannot be recycled while cached)
+# and its version counter (bumped by any in-place write); never used while a CUDA graph is captured.
+_KNN_CACHE = {}
+knn_cache_hits = 0
+
+
+def knn_cached(x: Tensor, k: int, sorted: bool = True) -> Tensor:
+    """knn_op with reuse of the previous result for an identical (storage, view, version, k) query.
+    Only small-C inputs (the xyz layer) are cached; ECB200_KNN_CACHE=0 disables it."""
+    global knn_cache_hits
+    if (x.shape[1] > 16 or os.environ.get("ECB200_KNN_CACHE", "1") == "0" or not x.is_cuda
+            or torch.cuda.is_current_stream_capturing()):
+        return knn_op(x, k, sorted)
+    st = x.untyped_storage()
+    key = (st.data_ptr(), x.storage_offset(), tuple(x.shape), tuple(x.stride()), x._version, int(k), x.dtype)
+    ent = _KNN_CACHE.get(x.device.index)
+    if ent is not None and ent[0] == key and (ent[3] or not sorted):
+        knn_cache_hits += 1
+        return ent[2]
+    idx = knn_op(x, k, sorted)
+    _KNN_CACHE[x.device.index] = (key, st, idx, bool(sorted))
+    return idx
+
+
 # ------------------------------------------------------------------------- autocast
 # Under torch.autocast (main_partseg_dist.py:253) the reference's bmm / conv2d would run in fp16
 # while its pow/sum and BatchNorm statistics stay fp32 (SURVEY.md §5).  The fused path always

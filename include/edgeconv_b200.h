@@ -271,6 +271,19 @@ size_t ecb200_peer_buffer_bytes(int world);
 int ecb200_peer_allreduce(double* vals, int n, void* const* peer_bufs, int rank, int world,
                           unsigned long long* seq_counter, void* stream);
 
+/* ---- two-conv edge block, fused forward (row f-1) ------------------------------------------
+ * Replaces, for inference, models/layers.py:45-52 of the reference (PositionEmbedding:
+ * get_graph_feature -> conv1 -> conv2 -> max over k) and upstream's two-conv EdgeConv blocks.
+ *   Y      [M, 2*C1]  the per-point GEMM of the FIRST conv, [U | V] (ecb200_point_gemm)
+ *   a1, b1 [C1]       BatchNorm1 folded to an affine (ecb200_bn_finalize)
+ *   w2hi/lo [C2, C1]  tf32 halves of the second conv's weight (ecb200_split_rows_tf32)
+ *   sel2   [M, C2]    max_j z_ij where gamma2 >= 0, min_j z_ij otherwise, z = W2.LeakyReLU(a1 e1 + b1)
+ *   stats2 [2*C2+1]   fp64, += [sum z | sum z^2 | edge count] (may be NULL); zero it first
+ * C1 in {32, 64}, C2 in {32, 64, 128}, k <= 128.  Finish with ecb200_bn_finalize + ecb200_edge_apply. */
+int ecb200_two_conv_fwd(const float* Y, const int32_t* idx, const float* a1, const float* b1,
+                        float slope1, const float* w2hi, const float* w2lo, const float* gamma2,
+                        int B, int N, int k, int C1, int C2, float* sel2, double* stats2, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -208,3 +208,29 @@ def test_external_idx_is_validated(ec):
         ec.get_graph_feature(x, k=4, idx=torch.zeros(1, 15, 4, dtype=torch.int64, device=dev()))
     with pytest.raises(TypeError):
         ec.get_graph_feature(x, k=4, idx=torch.zeros(1, 16, 4, device=dev()))
+
+
+@needs_ref
+def test_partseg_net_reuses_the_xyz_graph(ec, monkeypatch):
+    """row f-3 (part 1): the reference's Net asks for knn(src, k) on the same xyz tensor three times
+    per forward (dgcnn.py:84, model_partseg.py:26, layers.py:45); the drop-in answers two of them from
+    its one-entry cache, and an in-place change of the input invalidates it."""
+    from dgcnn_pytorch_b200.synthetic import synthetic_xyz
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    _, our_ps = ref_cls.reference_stack(_dropin_module(ec), "ours")
+    args = SimpleNamespace(k=8, emb_dim=64, n_heads=2, n_blocks=1, ff_dims=128, dropout=0.0, nclasses=50)
+    net = our_ps.Net(args).to(dev()).eval()
+    x = synthetic_xyz(2, 256, seed=4).to(dev())
+    lbl = torch.zeros(2, 16, device=dev())
+    lbl[:, 0] = 1.0
+    h0 = ec.ops.knn_cache_hits
+    with torch.no_grad():
+        net(x, lbl)
+    assert ec.ops.knn_cache_hits - h0 == 2
+    a = ec.knn(x, 8)
+    x.mul_(-1.0).add_(0.25 * torch.randn_like(x))            # in-place: version counter moves
+    b = ec.knn(x, 8)
+    assert not torch.equal(a, b)
+    import edgeconv_oracle as orc
+    rep = orc.knn_mismatch_report(x.cpu(), b.cpu(), orc.knn_oracle(x.cpu(), 8))
+    assert rep["bad_rows"] == 0, rep

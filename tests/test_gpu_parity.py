@@ -62,6 +62,12 @@ def assert_rel_modulo_arg_flips(ours, ref, group_dim, max_groups, rel=REL, what=
         return
     groups = int(bad.movedim(group_dim, -1).reshape(-1, bad.shape[group_dim]).any(dim=0).sum())
     err = (ours - ref).abs().max().item()
+    # record what was actually observed, so the allowance can be judged against it
+    log = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
+    if os.path.isdir(log):
+        with open(os.path.join(log, "arg_flips.log"), "a") as f:
+            f.write(f"{what}: {int(bad.sum())} elements in {groups} slices beyond {rel} (allowance {max_groups}), "
+                    f"max|diff| {err:.3e} vs scale {scale:.3e}\n")
     assert groups <= max_groups and err <= 0.05 * scale, (
         f"{what}: max|diff| {err:.3e} vs scale {scale:.3e}; {int(bad.sum())} elements in {groups} "
         f"slices violate {rel} (more than {max_groups} arg-max flips can explain)")
@@ -93,6 +99,9 @@ def test_knn_golden(ec, path):
     (32, 3, 1024, 20, "xyz"),        # BASELINE config 1, layer 1
     (4, 64, 1024, 20, "feat"),       # config 1, layers 2-3
     (2, 128, 1024, 20, "feat"),      # config 1, layer 4
+    (2, 64, 2048, 40, "feat"),       # config 2 / part-seg shape on the tensor cores
+    (1, 128, 4096, 20, "feat"),      # sem-seg shape (N = 4096) on the tensor cores
+    (3, 32, 200, 12, "feat"),        # odd number of row tiles, ragged last tile, C = 32
     (4, 3, 2048, 40, "xyz"),         # config 2
     (1, 128, 2048, 40, "feat"),
     (2, 3, 4096, 20, "xyz"),         # sem-seg shape (graph on the xyz slice)
