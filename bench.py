@@ -46,8 +46,10 @@ import torch  # noqa: E402
 
 METRIC = "DGCNN-cls fwd+bwd clouds/sec (N=1024,k=20)"
 UNIT = "clouds/s"
-CONV5_NOTE = ("conv5 GEMM in cuDNN (library default TF32) on the channels-last concat; its BatchNorm + "
-              "LeakyReLU + max|avg pooling in own kernels (embed_pool); 3 head linears in torch")
+CONV5_NOTE = ("conv5 forward = own tcgen05 GEMM (ecb200_embed_gemm) on the channels-last concat with the BatchNorm "
+              "statistics in its epilogue, plain TF32 on fp32 operands because torch.backends.cudnn.allow_tf32 is "
+              "on (PyTorch default; 3xTF32 when it is off); conv5 backward = library convolution backward (TF32); "
+              "BatchNorm + LeakyReLU + max|avg pooling in own kernels (embed_pool); 3 head linears in torch")
 
 
 def parse():
@@ -307,8 +309,8 @@ def gather_kernel_bytes(M, k, Co, training=True):
 
 
 # forward kernels of the EdgeConv path (kNN + edge MLP + max), by name fragments of the kernels
-EDGE_FWD_KERNELS = ("knn_tc_kernel", "knn_xyz_kernel", "knn_fma_kernel", "sqnorms_kernel", "split_tf32_kernel",
-                    "prepare_weights_kernel", "pack_weight_kernel", "gemm_tile_kernel", "edge_gather_kernel",
+EDGE_FWD_KERNELS = ("knn_tc_kernel<32, false", "knn_xyz_kernel", "knn_fma_kernel", "sqnorms_kernel", "split_tf32_kernel",
+                    "prepare_weights_kernel", "pack_weight_kernel", "gemm_tile_kernel", "knn_tc_kernel<32, true", "edge_gather_kernel",
                     "bn_finalize_kernel", "edge_apply_kernel", "bn_update_running_kernel")
 
 

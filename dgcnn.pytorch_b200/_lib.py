@@ -49,6 +49,7 @@ SIGNATURES = {
     "ecb200_colstats": (P, LL, I, P, P),
     "ecb200_embed_pool": (P, P, P, F, I, I, I, P, P, P),
     "ecb200_embed_pool_bwd_stats": (P, P, P, P, P, P, P, F, I, I, I, P, P),
+    "ecb200_embed_gemm": (P, P, P, P, LL, I, I, P, P, P),
     "ecb200_two_conv_fwd": (P, P, P, P, F, P, P, P, I, I, I, I, I, P, P, P),
     "ecb200_embed_pool_bwd_dz": (P, P, P, P, P, P, P, P, F, I, I, I, P, P),
 }

@@ -64,16 +64,20 @@ struct EpiDw {  // D[o, c] += into dWcat[o, c]
 // MN_MAJOR = false: A[M rows, K] and B[BN rows, K], K contiguous (TMA box 32 k x 128 rows).
 // MN_MAJOR = true : A[K rows, M'] and B[K rows, BN], rows = reduction index (TMA box 32 cols x
 //                   32 rows per 32-column atom).
+// `three` = 1: D += Ahi.Bhi + Ahi.Blo + Alo.Bhi (3xTF32, fp32-equivalent); 0: D += A.B in plain TF32 from
+// the `hi` maps only (which may then be the raw fp32 arrays: the tensor core reads their top 19 bits).
+// blockIdx.z = tile of BN output columns (rows [z*BN, +BN) of B).
 template <bool MN_MAJOR, class Epi>
 __global__ void __launch_bounds__(NT, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__ CUtensorMap a_lo,
                const __grid_constant__ CUtensorMap b_hi, const __grid_constant__ CUtensorMap b_lo,
-               int BN, long long K, long long kslab, Epi epi) {
+               int BN, long long K, long long kslab, int three, Epi epi) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   Tail* T = reinterpret_cast<Tail*>(base + (size_t)STAGES * 4 * SUB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x;                     // 128-row tile of the output
+  const int nt = blockIdx.z;                     // BN-column tile of the output
   const long long k_beg = (long long)blockIdx.y * kslab;
   const long long k_end = k_beg + kslab < K ? k_beg + kslab : K;
   const int nkb = (int)((k_end - k_beg + KB - 1) / KB);
@@ -93,42 +97,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
   const uint32_t b_bytes = (uint32_t)(BN * KB * 4);  // one half of the B stage
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&T->empty[stage], phase ^ 1);
+    // TMA producer: the whole warp stays in the loop, one elected lane issues (warp-uniform operands)
+    int stage = 0;
+    uint32_t phase = 0;
+    const int brow = nt * BN;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&T->empty[stage], phase ^ 1);
+      if (elect_one_sync()) {
         unsigned char* st = base + (size_t)stage * 4 * SUB;  // [A hi | A lo | B hi | B lo]
-        mbar_expect_tx(&T->full[stage], 2 * SUB + 2 * b_bytes);
+        mbar_expect_tx(&T->full[stage], three ? 2 * SUB + 2 * b_bytes : SUB + b_bytes);
         const int k0 = (int)(k_beg + (long long)kb * KB);
         if (!MN_MAJOR) {
           tma_load_2d(st, &a_hi, &T->full[stage], k0, mt * BM);
-          tma_load_2d(st + SUB, &a_lo, &T->full[stage], k0, mt * BM);
-          tma_load_2d(st + 2 * SUB, &b_hi, &T->full[stage], k0, 0);
-          tma_load_2d(st + 3 * SUB, &b_lo, &T->full[stage], k0, 0);
+          tma_load_2d(st + 2 * SUB, &b_hi, &T->full[stage], k0, brow);
+          if (three) {
+            tma_load_2d(st + SUB, &a_lo, &T->full[stage], k0, mt * BM);
+            tma_load_2d(st + 3 * SUB, &b_lo, &T->full[stage], k0, brow);
+          }
         } else {
           // one box per 32-column atom: 32 columns x 32 reduction rows = 4 KB
           for (int a = 0; a < BM / 32; ++a) {
             tma_load_2d(st + a * 4096, &a_hi, &T->full[stage], mt * BM + a * 32, k0);
-            tma_load_2d(st + SUB + a * 4096, &a_lo, &T->full[stage], mt * BM + a * 32, k0);
+            if (three) tma_load_2d(st + SUB + a * 4096, &a_lo, &T->full[stage], mt * BM + a * 32, k0);
           }
           for (int a = 0; a < BN / 32; ++a) {
-            tma_load_2d(st + 2 * SUB + a * 4096, &b_hi, &T->full[stage], a * 32, k0);
-            tma_load_2d(st + 3 * SUB + a * 4096, &b_lo, &T->full[stage], a * 32, k0);
+            tma_load_2d(st + 2 * SUB + a * 4096, &b_hi, &T->full[stage], brow + a * 32, k0);
+            if (three) tma_load_2d(st + 3 * SUB + a * 4096, &b_lo, &T->full[stage], brow + a * 32, k0);
           }
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32_major(BM, BN, MN_MAJOR, MN_MAJOR);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&T->full[stage], phase);
-        tc_fence_after();
-        const uint32_t st = smem_u32(base + (size_t)stage * 4 * SUB);
+    // MMA issuer: whole warp in the loop, one elected lane issues
+    const uint32_t idesc = make_idesc_tf32_major(BM, BN, MN_MAJOR, MN_MAJOR);
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, T->tmem_slot, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&T->full[stage], phase);
+      tc_fence_after();
+      const uint32_t st = smem_u32(base + (size_t)stage * 4 * SUB);
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
           uint64_t dah, dal, dbh, dbl;
@@ -145,14 +156,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
             dbh = make_sw128_mnmajor_desc(st + 2 * SUB + ko, 4096);
             dbl = make_sw128_mnmajor_desc(st + 3 * SUB + ko, 4096);
           }
-          mma_tf32(tmem_base, dah, dbh, idesc, (kb | k8) != 0);
-          mma_tf32(tmem_base, dah, dbl, idesc, 1);
-          mma_tf32(tmem_base, dal, dbh, idesc, 1);
+          mma_tf32(tmem_d, dah, dbh, idesc, (kb | k8) != 0);
+          if (three) {
+            mma_tf32(tmem_d, dah, dbl, idesc, 1);
+            mma_tf32(tmem_d, dal, dbh, idesc, 1);
+          }
         }
         mma_commit(&T->empty[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (kb + 1 == nkb) mma_commit(&T->done);
       }
-      mma_commit(&T->done);
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
     // ===================== epilogue (thread = output row) =====================
@@ -161,11 +175,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
     if (nkb > 0) {
       mbar_wait(&T->done, 0);
       tc_fence_after();
-      for (int c4 = 0; c4 < BN / 32; ++c4) {
-        float v[32];
-        __syncwarp();
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c4 * 32), v);
-        epi.store(mt * BM + r, c4 * 32, v);
+      if constexpr (Epi::STAGED) {
+        // the operand ring is dead: stage the 128 x BN tile there ([128][BN+1] floats), then let the
+        // epilogue reduce columns / write whole rows from shared memory
+        float* zs = reinterpret_cast<float*>(base);
+        const int ld = BN + 1;
+        for (int c4 = 0; c4 < BN / 32; ++c4) {
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c4 * 32), v);
+#pragma unroll
+          for (int u = 0; u < 32; ++u) zs[r * ld + c4 * 32 + u] = v[u];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        epi.finish(zs, ld, mt * BM, nt * BN, BN, (int)threadIdx.x - 64);
+      } else {
+        for (int c4 = 0; c4 < BN / 32; ++c4) {
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c4 * 32), v);
+          epi.store(mt * BM + r, c4 * 32, v);
+        }
       }
     }
   }
@@ -175,6 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
 }
 
 struct EpiDxImpl : EpiDx {
+  static constexpr bool STAGED = false;
   __device__ __forceinline__ void store(long long m, int c0, const float (&v)[32]) const {
     if (m >= M) return;
     const long long b = m / N;
@@ -186,12 +217,42 @@ struct EpiDxImpl : EpiDx {
   }
 };
 struct EpiDwImpl : EpiDw {
+  static constexpr bool STAGED = false;
   __device__ __forceinline__ void store(long long o, int c0, const float (&v)[32]) const {
     if (o >= rows) return;
     float* p = dW + (size_t)o * C + c0;
 #pragma unroll
     for (int u = 0; u < 32; ++u)
       if (c0 + u < C) atomicAdd(p + u, v[u]);
+  }
+};
+
+// Z[m, n0 + c] = D (row-major, whole 512-byte rows per warp instruction) and, per output column, the
+// sum and sum of squares over the tile's rows (BatchNorm statistics of conv5, fp64 atomics): the
+// statistics pass over the 128 MiB result and its re-read disappear.
+struct EpiRowStats {
+  static constexpr bool STAGED = true;
+  float* Z; long long M; int ldz; double* stats; int E;
+  __device__ __forceinline__ void finish(const float* zs, int ld, long long m0, int n0, int BN, int t) const {
+    const int rows = (int)(M - m0 < BM ? M - m0 : BM);
+    if (stats) {   // thread t = column t of the tile
+      if (t < BN) {
+        float s = 0.f, q = 0.f;
+        for (int r = 0; r < rows; ++r) {
+          const float z = zs[r * ld + t];
+          s += z;
+          q = fmaf(z, z, q);
+        }
+        atomicAdd(stats + n0 + t, (double)s);
+        atomicAdd(stats + E + n0 + t, (double)q);
+      }
+      if (m0 == 0 && n0 == 0 && t == 0) atomicAdd(stats + 2 * E, (double)M);
+    }
+    const int w = t >> 5, l = t & 31;   // warp w writes rows w, w+4, ...: one coalesced row segment each
+    for (int r = w; r < rows; r += 4) {
+      float* o = Z + (size_t)(m0 + r) * ldz + n0;
+      for (int c = l; c < BN; c += 32) o[c] = zs[r * ld + c];
+    }
   }
 };
 
@@ -280,7 +341,7 @@ extern "C" int ecb200_gemm_dx_tc(const float* dYhi, const float* dYlo, const flo
   EpiDxImpl epi;
   epi.dx = dx; epi.C = C; epi.N = N; epi.M = M;
   dim3 grid((unsigned)ecb200::ceil_div64(M, BM), 1);
-  kern<<<grid, NT, SMEM_BYTES, (cudaStream_t)stream>>>(ah, al, bh, bl, C, (long long)Co2, (long long)Co2, epi);
+  kern<<<grid, NT, SMEM_BYTES, (cudaStream_t)stream>>>(ah, al, bh, bl, C, (long long)Co2, (long long)Co2, 1, epi);
   ECB_LAUNCH_CHECK("gemm_tc_kernel<dx>");
   return ECB200_OK;
 }
@@ -310,7 +371,35 @@ extern "C" int ecb200_gemm_dw_tc(const float* dYhi, const float* dYlo, const flo
   EpiDwImpl epi;
   epi.dW = dWcat; epi.C = C; epi.rows = Co2;
   dim3 grid(mtiles, (unsigned)slabs);
-  kern<<<grid, NT, SMEM_BYTES, st>>>(ah, al, bh, bl, C, M, kslab, epi);
+  kern<<<grid, NT, SMEM_BYTES, st>>>(ah, al, bh, bl, C, M, kslab, 1, epi);
   ECB_LAUNCH_CHECK("gemm_tc_kernel<dw>");
+  return ECB200_OK;
+}
+
+// conv5 of the backbone (models/dgcnn.py:74-78,:102) as a per-point GEMM with its BatchNorm statistics
+// in the epilogue: Z[M, E] = X[M, K] . W[E, K]^T, stats += [sum z | sum z^2 | M].  xlo / wlo NULL selects
+// plain TF32 on the raw fp32 operands (what the library convolution does with cudnn.allow_tf32, the
+// PyTorch default); with the tf32 halves of both operands the product is 3xTF32 (fp32-equivalent).
+extern "C" int ecb200_embed_gemm(const float* xhi, const float* xlo, const float* whi, const float* wlo,
+                                 long long M, int K, int E, float* Z, double* stats, void* stream) {
+  ECB_REQUIRE(xhi && whi && Z, "ecb200_embed_gemm: null pointer");
+  ECB_REQUIRE((xlo == nullptr) == (wlo == nullptr), "ecb200_embed_gemm: the lo halves come in pairs");
+  ECB_REQUIRE(M >= 1 && K >= KB && K % KB == 0 && E >= 128 && E % 128 == 0,
+              "ecb200_embed_gemm: needs K a multiple of 32 and E a multiple of 128 (K=%d E=%d)", K, E);
+  const int three = xlo != nullptr;
+  CUtensorMap ah, al, bh, bl;
+  int rc;
+  if ((rc = make_map(&ah, xhi, M, K, KB, BM))) return rc;
+  if ((rc = make_map(&al, three ? xlo : xhi, M, K, KB, BM))) return rc;
+  if ((rc = make_map(&bh, whi, E, K, KB, 128))) return rc;
+  if ((rc = make_map(&bl, three ? wlo : whi, E, K, KB, 128))) return rc;
+  auto kern = gemm_tc_kernel<false, EpiRowStats>;
+  static thread_local bool seen[ecb200::kMaxDevices] = {};
+  if ((rc = opt_in_smem(kern, seen))) return rc;
+  EpiRowStats epi;
+  epi.Z = Z; epi.M = M; epi.ldz = E; epi.stats = stats; epi.E = E;
+  dim3 grid((unsigned)ecb200::ceil_div64(M, BM), 1, (unsigned)(E / 128));
+  kern<<<grid, NT, SMEM_BYTES, (cudaStream_t)stream>>>(ah, al, bh, bl, 128, (long long)K, (long long)K, three, epi);
+  ECB_LAUNCH_CHECK("gemm_tc_kernel<embed>");
   return ECB200_OK;
 }

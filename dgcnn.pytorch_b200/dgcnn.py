@@ -198,8 +198,18 @@ class DGCNN(nn.Module):
         BatchNorm + LeakyReLU are fused with the pooling, so the [B, emb, N] tensor never exists."""
         batch_size, _, num_points = x.size()
         conv, bn, act = self.conv5[0], self.conv5[1], self.conv5[2]
-        z = conv(self._edge_features(x, idx_list))                       # [B,emb,N,1], channels-last
-        z = z.permute(0, 2, 3, 1).reshape(batch_size * num_points, -1)    # [B*N, emb] (a view)
+        feats = self._edge_features(x, idx_list)                          # [B,512,N,1], channels-last
+        mode = ops.embed_gemm_mode(conv.in_channels, conv.out_channels)
+        stats = None
+        if mode != "cudnn" and conv.bias is None and feats.dtype == torch.float32:
+            # conv5 as a per-point GEMM on the tensor cores, BatchNorm statistics from its epilogue
+            x_pm = feats.permute(0, 2, 3, 1).reshape(batch_size * num_points, -1)   # [B*N, 512] (a view)
+            z, stats = ops.embed_gemm_op(x_pm, conv.weight, mode == "3xtf32")
+            if not (bn.training or bn.running_mean is None):
+                stats = None
+        else:
+            z = conv(feats)                                                # library convolution
+            z = z.permute(0, 2, 3, 1).reshape(batch_size * num_points, -1)    # [B*N, emb] (a view)
         return ops.embed_pool(z, batch_size, num_points, bn.weight, bn.bias, bn.running_mean,
                               bn.running_var, bn.num_batches_tracked, bn.training, bn.momentum, bn.eps,
-                              float(getattr(act, "negative_slope", 0.0)), _sync_group(bn))
+                              float(getattr(act, "negative_slope", 0.0)), _sync_group(bn), stats)

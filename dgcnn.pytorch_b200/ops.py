@@ -499,7 +499,8 @@ def edgeconv(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor
 @torch.library.custom_op("edgeconv_b200::embed_pool_fwd", mutates_args=(), device_types="cuda")
 def embed_pool_fwd_op(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor,
                       running_mean: Optional[Tensor], running_var: Optional[Tensor],
-                      use_batch_stats: bool, eps: float, slope: float, group: int) -> List[Tensor]:
+                      use_batch_stats: bool, eps: float, slope: float, group: int,
+                      stats_in: Optional[Tensor] = None) -> List[Tensor]:
     """z [B*N, E] (conv5's raw output, point-major) -> [pooled [B,2E], arg [B,E] i32,
     affine [4,E] = (mean, invstd, a, b), stats [2E+1] f64]:  pooled = (max_n | mean_n) of
     LeakyReLU(BatchNorm(z)) -- dgcnn.py:75-78,:102 followed by upstream DGCNN_cls's pooling."""
@@ -515,13 +516,16 @@ def embed_pool_fwd_op(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor,
     with torch.cuda.device(dev):
         st = _stream(z)
         f32 = dict(device=dev, dtype=torch.float32)
-        stats = torch.zeros(2 * E + 1, device=dev, dtype=torch.float64)
+        # [sum z | sum z^2 | count]: from the GEMM's epilogue (ecb200_embed_gemm) when it produced z
+        stats = (stats_in.clone() if stats_in is not None
+                 else torch.zeros(2 * E + 1, device=dev, dtype=torch.float64))
         affine = torch.empty(4, E, **f32)
         mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * E * r) for r in range(4))
         pooled = torch.empty(B, 2 * E, **f32)
         arg = torch.empty(B, E, device=dev, dtype=torch.int32)
         if use_batch_stats:
-            _lib.call("ecb200_colstats", _ptr(z), M, E, _ptr(stats), st)
+            if stats_in is None:
+                _lib.call("ecb200_colstats", _ptr(z), M, E, _ptr(stats), st)
             if group:
                 _allreduce_stats(stats, group)
         _lib.call("ecb200_bn_finalize", _ptr(stats), _ptr(gamma_c), _ptr(beta_c),
@@ -533,7 +537,7 @@ def embed_pool_fwd_op(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor,
 
 
 @embed_pool_fwd_op.register_fake
-def _(z, B, N, gamma, beta, running_mean, running_var, use_batch_stats, eps, slope, group):
+def _(z, B, N, gamma, beta, running_mean, running_var, use_batch_stats, eps, slope, group, stats_in=None):
     E = z.shape[1]
     f = z.new_empty
     return [f((B, 2 * E)), f((B, E), dtype=torch.int32), f((4, E)), f((2 * E + 1,), dtype=torch.float64)]
@@ -577,7 +581,7 @@ def _(gpool, z, arg, affine, stats, B, N, use_batch_stats, slope, group):
 
 
 def _ep_setup(ctx, inputs, output):
-    z, B, N, _g, _b, _rm, _rv, use_batch_stats, _eps, slope, group = inputs
+    z, B, N, _g, _b, _rm, _rv, use_batch_stats, _eps, slope, group = inputs[:11]
     _pooled, arg, affine, stats = output
     ctx.save_for_backward(z, arg, affine, stats)
     ctx.cfg = (B, N, use_batch_stats, slope, group)
@@ -587,11 +591,11 @@ def _ep_setup(ctx, inputs, output):
 def _ep_backward(ctx, grads):
     gpool = grads[0]
     if gpool is None:
-        return (None,) * 11
+        return (None,) * 12
     z, arg, affine, stats = ctx.saved_tensors
     B, N, use_batch_stats, slope, group = ctx.cfg
     dz, dgamma, dbeta = embed_pool_bwd_op(gpool, z, arg, affine, stats, B, N, use_batch_stats, slope, group)
-    return (dz, None, None, dgamma, dbeta) + (None,) * 6
+    return (dz, None, None, dgamma, dbeta) + (None,) * 7
 
 
 embed_pool_fwd_op.register_autograd(_ep_backward, setup_context=_ep_setup)
@@ -600,17 +604,92 @@ embed_pool_fwd_op.register_autograd(_ep_backward, setup_context=_ep_setup)
 def embed_pool(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor, running_mean: Optional[Tensor],
                running_var: Optional[Tensor], num_batches_tracked: Optional[Tensor], training: bool,
                momentum: Optional[float] = 0.1, eps: float = 1e-5, slope: float = 0.2,
-               group: int = 0) -> Tensor:
+               group: int = 0, stats: Optional[Tensor] = None) -> Tensor:
     """cat(max_n, mean_n) of LeakyReLU(BatchNorm(z)) over the N points of each cloud -> [B, 2E].
-    z [B*N, E] point-major; BatchNorm semantics as nn.BatchNorm2d / SyncBatchNorm (see edgeconv)."""
+    z [B*N, E] point-major; BatchNorm semantics as nn.BatchNorm2d / SyncBatchNorm (see edgeconv).
+    ``stats``: this rank's [sum z | sum z^2 | count] if the producer of z already has them."""
     use_batch_stats = bool(training or running_mean is None or running_var is None)
     update_running = bool(training and running_mean is not None)
     mom = -1.0 if momentum is None else float(momentum)
     res = embed_pool_fwd_op(z, int(B), int(N), gamma, beta, running_mean, running_var, use_batch_stats,
-                            float(eps), float(slope), int(group))
+                            float(eps), float(slope), int(group), stats.detach() if stats is not None else None)
     if update_running:
         bn_update_running_op(res[3].detach(), running_mean, running_var, num_batches_tracked, mom)
     return res[0]
+
+
+# ------------------------------------------------ conv5 as a per-point GEMM with BN statistics
+def embed_gemm_mode(K: int, E: int) -> str:
+    """How conv5's GEMM runs: "tf32" (own tcgen05 kernel, plain TF32 on the raw fp32 operands -- the
+    precision class of the library convolution under torch.backends.cudnn.allow_tf32, PyTorch's
+    default), "3xtf32" (own kernel, fp32-equivalent; chosen when allow_tf32 is off) or "cudnn"
+    (library convolution: unsupported shape, or ECB200_CONV5=cudnn)."""
+    mode = os.environ.get("ECB200_CONV5", "auto")
+    if mode == "cudnn" or K % 32 != 0 or E % 128 != 0:
+        return "cudnn"
+    if mode in ("tf32", "3xtf32"):
+        return mode
+    return "tf32" if torch.backends.cudnn.allow_tf32 else "3xtf32"
+
+
+@torch.library.custom_op("edgeconv_b200::embed_gemm", mutates_args=(), device_types="cuda")
+def embed_gemm_op(x_pm: Tensor, weight: Tensor, three: bool) -> List[Tensor]:
+    """x_pm [M,K] (the channels-last concat of dgcnn.py:100), weight [E,K,1,1] (conv5) ->
+    [z [M,E] = x_pm . W^T, stats [2E+1] f64 = [sum z | sum z^2 | M]]  (ecb200_embed_gemm)."""
+    _check_cuda_f32("x_pm", x_pm, 2)
+    M, K = x_pm.shape
+    E = weight.shape[0]
+    x_pm = x_pm.contiguous()
+    w = weight.detach().reshape(E, K).contiguous().float()
+    dev = x_pm.device
+    with torch.cuda.device(dev):
+        st = _stream(x_pm)
+        z = torch.empty(M, E, device=dev, dtype=torch.float32)
+        stats = torch.zeros(2 * E + 1, device=dev, dtype=torch.float64)
+        if three:
+            xs = torch.empty(2, M, K, device=dev, dtype=torch.float32)
+            ws = torch.empty(2, E, K, device=dev, dtype=torch.float32)
+            _lib.call("ecb200_split_rows_tf32", _ptr(x_pm), M * K, _ptr(xs[0]), _ptr(xs[1]), st)
+            _lib.call("ecb200_split_rows_tf32", _ptr(w), E * K, _ptr(ws[0]), _ptr(ws[1]), st)
+            _lib.call("ecb200_embed_gemm", _ptr(xs[0]), _ptr(xs[1]), _ptr(ws[0]), _ptr(ws[1]), M, K, E, _ptr(z),
+                      _ptr(stats), st)
+        else:
+            _lib.call("ecb200_embed_gemm", _ptr(x_pm), None, _ptr(w), None, M, K, E, _ptr(z), _ptr(stats), st)
+    return [z, stats]
+
+
+@embed_gemm_op.register_fake
+def _(x_pm, weight, three):
+    M, E = x_pm.shape[0], weight.shape[0]
+    return [x_pm.new_empty((M, E)), x_pm.new_empty((2 * E + 1,), dtype=torch.float64)]
+
+
+def _eg_setup(ctx, inputs, output):
+    x_pm, weight, _three = inputs
+    ctx.save_for_backward(x_pm, weight)
+    ctx.set_materialize_grads(False)
+
+
+def _eg_backward(ctx, grads):
+    gz = grads[0]
+    if gz is None:
+        return None, None, None
+    x_pm, weight = ctx.saved_tensors
+    M, K = x_pm.shape
+    E = weight.shape[0]
+    # the two backward GEMMs stay plain library calls -- the convolution backward on channels-last
+    # views, exactly what autograd ran before this op existed (same TF32 policy as the reference)
+    x4 = x_pm.view(1, M, 1, K).permute(0, 3, 1, 2)
+    g4 = gz.contiguous().view(1, M, 1, E).permute(0, 3, 1, 2)
+    dx4, dw4, _ = torch.ops.aten.convolution_backward(
+        g4, x4, weight.reshape(E, K, 1, 1), None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1,
+        [bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]), False])
+    dx = dx4.permute(0, 2, 3, 1).reshape(M, K) if dx4 is not None else None
+    dw = dw4.reshape(weight.shape) if dw4 is not None else None
+    return dx, dw, None
+
+
+embed_gemm_op.register_autograd(_eg_backward, setup_context=_eg_setup)
 
 
 # ---------------------------------------------------- two-conv edge block, fused forward (row f-1)
@@ -737,7 +816,7 @@ def knn_cached(x: Tensor, k: int, sorted: bool = True) -> Tensor:
 # and runs with autocast disabled.  Gradients are linear in the incoming gradient, so GradScaler's
 # loss scaling and its inf/nan detection pass through unchanged.
 for _op in (knn_op, split_tf32_op, knn_tc_op, graph_feature_op, graph_feature_bwd_op, edgeconv_fwd_op,
-            edgeconv_bwd_op, embed_pool_fwd_op, embed_pool_bwd_op):
+            edgeconv_bwd_op, embed_pool_fwd_op, embed_pool_bwd_op, embed_gemm_op):
     _op.register_autocast("cuda", torch.float32)
 
 

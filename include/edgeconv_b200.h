@@ -271,6 +271,16 @@ size_t ecb200_peer_buffer_bytes(int world);
 int ecb200_peer_allreduce(double* vals, int n, void* const* peer_bufs, int rank, int world,
                           unsigned long long* seq_counter, void* stream);
 
+/* conv5 of the backbone (models/dgcnn.py:74-78 applied at :102) as a per-point GEMM on the tensor cores
+ * with its BatchNorm statistics in the epilogue: Z[M,E] = X[M,K] . W[E,K]^T (X = the channels-last
+ * 512-channel concat of dgcnn.py:100), stats[2E+1] (fp64, zeroed by the caller; may be NULL) +=
+ * [sum z | sum z^2 | M] in the layout ecb200_bn_finalize consumes.  xlo = wlo = NULL: plain TF32 on the
+ * raw fp32 operands (the precision class of the library convolution under cudnn.allow_tf32, PyTorch's
+ * default); with the tf32 halves (ecb200_split_rows_tf32) of both operands: 3xTF32, fp32-equivalent.
+ * K a multiple of 32, E a multiple of 128. */
+int ecb200_embed_gemm(const float* xhi, const float* xlo, const float* whi, const float* wlo,
+                      long long M, int K, int E, float* Z, double* stats, void* stream);
+
 /* ---- two-conv edge block, fused forward (row f-1) ------------------------------------------
  * Replaces, for inference, models/layers.py:45-52 of the reference (PositionEmbedding:
  * get_graph_feature -> conv1 -> conv2 -> max over k) and upstream's two-conv EdgeConv blocks.

@@ -162,3 +162,32 @@ def test_semseg_model_eval_vs_oracle(ec):
     # require 99.9 % of the logits within 1e-3 of the scale and all of them within 5e-2
     err = (out.cpu() - exp).abs() / exp.abs().max()
     assert (err <= 1e-3).float().mean().item() >= 0.999 and err.max().item() < 5e-2, (err.max().item(),)
+
+
+# ------------------------------------------------------------------ conv5 GEMM (row f-2)
+@pytest.mark.parametrize("M,K,E,three", [(4096, 512, 1024, True), (4096, 512, 1024, False), (1000, 64, 128, True),
+                                         (333, 512, 256, False)])
+def test_embed_gemm_forward_stats_backward(ec, M, K, E, three):
+    """conv5 as a per-point GEMM (ecb200_embed_gemm): values and the BatchNorm statistics of its
+    epilogue against fp64; 3xTF32 within 2e-5 of the scale, plain TF32 within 2e-3 (its precision
+    class: what the library convolution delivers under cudnn.allow_tf32); the backward (library
+    convolution backward) against autograd of F.conv2d."""
+    g = torch.Generator().manual_seed(M + E)
+    x = torch.randn(M, K, generator=g).to(dev()).requires_grad_(True)
+    w = (torch.randn(E, K, 1, 1, generator=g) / K ** 0.5).to(dev()).requires_grad_(True)
+    z, stats = ec.ops.embed_gemm_op(x, w, three)
+    ref = x.detach().double() @ w.detach().double().view(E, K).t()
+    tol = 2e-5 if three else 2e-3
+    assert (z.double() - ref).abs().max().item() <= tol * ref.abs().max().item()
+    zs = z.detach().double()
+    assert torch.allclose(stats[:E], zs.sum(0), rtol=1e-5, atol=1e-3 * zs.abs().max().item())
+    assert torch.allclose(stats[E:2 * E], (zs * zs).sum(0), rtol=1e-5)
+    assert float(stats[2 * E]) == M
+    gz = torch.randn(M, E, generator=g).to(dev())
+    (z * gz).sum().backward()
+    x2 = x.detach().clone().requires_grad_(True)
+    w2 = w.detach().clone().requires_grad_(True)
+    z2 = F.conv2d(x2.view(1, M, 1, K).permute(0, 3, 1, 2), w2).permute(0, 2, 3, 1).reshape(M, E)
+    (z2 * gz).sum().backward()
+    assert (x.grad - x2.grad).abs().max().item() <= 1e-4 * x2.grad.abs().max().item()
+    assert (w.grad - w2.grad).abs().max().item() <= 1e-4 * w2.grad.abs().max().item()
