@@ -46,6 +46,8 @@ SIGNATURES = {
     "ecb200_gemm_dx_tc": (P, P, P, P, I, I, I, I, P, P),
     "ecb200_gemm_dw_tc": (P, P, P, P, LL, I, I, P, P),
     "ecb200_peer_allreduce": (P, I, P, I, I, P, P),
+    "ecb200_peer_allreduce_bn_finalize": (P, I, P, I, I, P, P, P, F, P, P, P, P, P),
+    "ecb200_peer_allreduce_bwd_finalize": (P, P, I, P, I, I, P, P, P, P, P, P, P, P, P),
     "ecb200_colstats": (P, LL, I, P, P),
     "ecb200_embed_pool": (P, P, P, F, I, I, I, P, P, P),
     "ecb200_embed_pool_bwd_stats": (P, P, P, P, P, P, P, F, I, I, I, P, P),

@@ -31,9 +31,23 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
   return v;
 }
 
+// What the exchange feeds.  Every exchange of the path is followed by a tiny per-channel "finalize"
+// (BatchNorm affine in the forward, the c1/c2 coefficients in the backward); doing it in the same
+// kernel saves one launch per exchange -- twelve per training step.
+struct Finalize {
+  int kind;            // 0 none, 1 forward (ecb200_bn_finalize, training), 2 backward (ecb200_bwd_finalize, training)
+  int Co;
+  float eps;
+  const float *gamma, *beta;           // kind 1
+  float *mean, *invstd, *a, *b;        // kind 1 outputs
+  const double *local, *count;         // kind 2: this rank's [sum g | sum g*xhat]; global edge count
+  const float *a_in, *invstd_in;       // kind 2
+  float *dgamma, *dbeta, *c1, *c2;     // kind 2 outputs
+};
+
 __global__ void __launch_bounds__(512)
 peer_allreduce_kernel(double* __restrict__ vals, int n, void* const* __restrict__ peer_bufs, int rank,
-                      int world, unsigned long long* __restrict__ seq_counter) {
+                      int world, unsigned long long* __restrict__ seq_counter, Finalize fin) {
   constexpr size_t MAXV = ECB200_PEER_MAX_VALUES;
   const unsigned long long seq = *seq_counter + 1;
   const unsigned long long tag = (seq & 0xffffffffull) << 32;
@@ -65,6 +79,28 @@ peer_allreduce_kernel(double* __restrict__ vals, int n, void* const* __restrict_
   }
   __syncthreads();
   if (threadIdx.x == 0) *seq_counter = seq;
+  if (fin.kind == 1) {          // == bn_finalize_kernel (training) on the reduced statistics
+    const double count = vals[2 * fin.Co];
+    for (int o = threadIdx.x; o < fin.Co; o += blockDim.x) {
+      const double mu = vals[o] / count;
+      double var = vals[fin.Co + o] / count - mu * mu;
+      if (var < 0.0) var = 0.0;
+      const double r = 1.0 / sqrt(var + (double)fin.eps);
+      const double aa = (double)fin.gamma[o] * r;
+      fin.mean[o] = (float)mu;
+      fin.invstd[o] = (float)r;
+      fin.a[o] = (float)aa;
+      fin.b[o] = (float)((double)fin.beta[o] - aa * mu);
+    }
+  } else if (fin.kind == 2) {   // == bwd_finalize_kernel (training): vals = the reduced [sum g | sum g*xhat]
+    const double count = *fin.count;
+    for (int o = threadIdx.x; o < fin.Co; o += blockDim.x) {
+      fin.dbeta[o] = (float)fin.local[o];
+      fin.dgamma[o] = (float)fin.local[fin.Co + o];
+      fin.c1[o] = (float)((double)fin.a_in[o] * vals[o] / count);
+      fin.c2[o] = (float)((double)fin.a_in[o] * vals[fin.Co + o] * (double)fin.invstd_in[o] / count);
+    }
+  }
 }
 
 }  // namespace
@@ -79,7 +115,41 @@ extern "C" int ecb200_peer_allreduce(double* vals, int n, void* const* peer_bufs
   ECB_REQUIRE(n >= 1 && n <= ECB200_PEER_MAX_VALUES, "ecb200_peer_allreduce: n=%d outside [1, %d]", n,
               ECB200_PEER_MAX_VALUES);
   ECB_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "ecb200_peer_allreduce: bad rank/world");
-  peer_allreduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(vals, n, peer_bufs, rank, world, seq_counter);
+  Finalize fin = {};
+  peer_allreduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(vals, n, peer_bufs, rank, world, seq_counter, fin);
   ECB_LAUNCH_CHECK("peer_allreduce_kernel");
+  return ECB200_OK;
+}
+
+extern "C" int ecb200_peer_allreduce_bn_finalize(double* stats, int Co, void* const* peer_bufs, int rank,
+                                                 int world, unsigned long long* seq_counter,
+                                                 const float* gamma, const float* beta, float eps, float* mean,
+                                                 float* invstd, float* a, float* b, void* stream) {
+  ECB_REQUIRE(stats && peer_bufs && seq_counter && gamma && beta && mean && invstd && a && b,
+              "ecb200_peer_allreduce_bn_finalize: null pointer");
+  ECB_REQUIRE(Co >= 1 && 2 * Co + 1 <= ECB200_PEER_MAX_VALUES, "ecb200_peer_allreduce_bn_finalize: Co=%d", Co);
+  ECB_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "ecb200_peer_allreduce_bn_finalize: bad rank/world");
+  Finalize fin = {};
+  fin.kind = 1; fin.Co = Co; fin.eps = eps; fin.gamma = gamma; fin.beta = beta;
+  fin.mean = mean; fin.invstd = invstd; fin.a = a; fin.b = b;
+  peer_allreduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(stats, 2 * Co + 1, peer_bufs, rank, world, seq_counter, fin);
+  ECB_LAUNCH_CHECK("peer_allreduce_kernel<bn_finalize>");
+  return ECB200_OK;
+}
+
+extern "C" int ecb200_peer_allreduce_bwd_finalize(const double* bstats_local, double* bstats_global, int Co,
+                                                  void* const* peer_bufs, int rank, int world,
+                                                  unsigned long long* seq_counter, const double* count_dev,
+                                                  const float* a, const float* invstd, float* dgamma, float* dbeta,
+                                                  float* c1, float* c2, void* stream) {
+  ECB_REQUIRE(bstats_local && bstats_global && peer_bufs && seq_counter && count_dev && a && invstd && dgamma &&
+                  dbeta && c1 && c2, "ecb200_peer_allreduce_bwd_finalize: null pointer");
+  ECB_REQUIRE(Co >= 1 && 2 * Co <= ECB200_PEER_MAX_VALUES, "ecb200_peer_allreduce_bwd_finalize: Co=%d", Co);
+  ECB_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "ecb200_peer_allreduce_bwd_finalize: bad rank/world");
+  Finalize fin = {};
+  fin.kind = 2; fin.Co = Co; fin.local = bstats_local; fin.count = count_dev; fin.a_in = a; fin.invstd_in = invstd;
+  fin.dgamma = dgamma; fin.dbeta = dbeta; fin.c1 = c1; fin.c2 = c2;
+  peer_allreduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(bstats_global, 2 * Co, peer_bufs, rank, world, seq_counter, fin);
+  ECB_LAUNCH_CHECK("peer_allreduce_kernel<bwd_finalize>");
   return ECB200_OK;
 }

@@ -59,13 +59,15 @@ def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
 class FlatGradSync:
     """Data-parallel gradient averaging over a flat fp32 buffer, overlapped with the backward.
 
-    Every parameter's ``.grad`` is a view into ``self.flat``; autograd accumulates into the
-    views in place.  The parameters are laid out in two buckets: ``late`` (those whose
-    gradients are produced at the very end of the backward pass -- the EdgeConv layers, which
-    come first in the network) and ``early`` (conv5 and the head: 95 % of the bytes, complete
-    after the first few per cent of the backward).  As soon as the last ``early`` gradient has
-    been accumulated, its all-reduce is issued on a side stream and runs under the EdgeConv
-    backward; ``average()`` reduces the small ``late`` bucket and joins the side stream.
+    The parameters are laid out in one flat buffer in two buckets: ``late`` (those whose gradients
+    are produced at the very end of the backward pass -- the EdgeConv layers, which come first in the
+    network) and ``early`` (conv5 and the head: 95 % of the bytes, complete after the first few per
+    cent of the backward).  Autograd produces each gradient in its own tensor (``.grad`` is None at
+    the start of a step, so nothing is accumulated in place: no read-modify-write kernel per
+    parameter); a bucket is packed into the flat buffer by ONE multi-tensor copy as soon as its last
+    gradient exists.  The early bucket's all-reduce is issued on a side stream and runs under the
+    EdgeConv backward; ``average()`` packs and reduces the small late bucket, joins the side stream
+    and points every ``.grad`` at its (averaged) slice of the flat buffer for the optimizer.
     No bucketing threads; everything is capturable in a CUDA graph together with the step.
     Usage per step:  sync.zero() ; loss.backward() ; sync.average() ; optimizer.step()
     """
@@ -78,29 +80,42 @@ class FlatGradSync:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         if late is None:
             late = lambda i, p: i < 12  # noqa: E731
-        late_ps = [p for i, p in enumerate(self.params) if late(i, p)]
-        early_ps = [p for i, p in enumerate(self.params) if not late(i, p)]
+        self.late_ps = [p for i, p in enumerate(self.params) if late(i, p)]
+        self.early_ps = [p for i, p in enumerate(self.params) if not late(i, p)]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.view = {}
         o = 0
-        for p in late_ps + early_ps:
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+        for p in self.late_ps + self.early_ps:
+            self.view[p] = self.flat[o:o + p.numel()].view_as(p)
             o += p.numel()
-        n_late = sum(p.numel() for p in late_ps)
+        n_late = sum(p.numel() for p in self.late_ps)
         self.flat_late, self.flat_early = self.flat[:n_late], self.flat[n_late:]
-        self.overlap = bool(overlap and self.world > 1 and early_ps and dev.type == "cuda")
-        self._pending = len(early_ps)
+        self.overlap = bool(overlap and self.world > 1 and self.early_ps and dev.type == "cuda")
+        self._pending = len(self.early_ps)
         self._left = self._pending
         self._early_done = False
         self._side = torch.cuda.Stream(device=dev) if self.overlap else None
         if self.overlap:
-            for p in early_ps:
+            for p in self.early_ps:
                 p.register_post_accumulate_grad_hook(self._on_early_grad)
+        self.zero()
+
+    def _pack(self, ps) -> None:
+        """gradients of ``ps`` -> their slices of the flat buffer (one multi-tensor copy); a parameter
+        that received no gradient contributes zeros"""
+        have = [p for p in ps if p.grad is not None and p.grad.data_ptr() != self.view[p].data_ptr()]
+        if have:
+            torch._foreach_copy_([self.view[p] for p in have], [p.grad for p in have])
+        for p in ps:
+            if p.grad is None:
+                self.view[p].zero_()
 
     def _on_early_grad(self, _param) -> None:
         self._left -= 1
         if self._left == 0:
+            self._pack(self.early_ps)
             cur = torch.cuda.current_stream()
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
@@ -109,21 +124,26 @@ class FlatGradSync:
             self._early_done = True
 
     def zero(self) -> None:
-        self.flat.zero_()
+        """start of a step: every ``.grad`` is None, so autograd stores (not accumulates) gradients"""
+        for p in self.params:
+            p.grad = None
         self._left = self._pending
         self._early_done = False
 
     def average(self) -> None:
-        if self.world <= 1:
-            return
         if self._early_done:
+            self._pack(self.late_ps)
             if self.flat_late.numel():
                 dist.all_reduce(self.flat_late, op=dist.ReduceOp.SUM, group=self.group)
                 self.flat_late.mul_(1.0 / self.world)
             torch.cuda.current_stream().wait_stream(self._side)
-        else:   # hooks did not fire (e.g. a parameter got no gradient): reduce everything here
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.mul_(1.0 / self.world)
+        else:   # no overlap (or a hook did not fire): pack and reduce everything here
+            self._pack(self.params)
+            if self.world > 1:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.mul_(1.0 / self.world)
+        for p in self.params:
+            p.grad = self.view[p]
 
 
 class PeerStatsExchange:

@@ -64,6 +64,40 @@ def _allreduce_stats(stats: Tensor, handle: int) -> None:
         dist.all_reduce(stats, group=_GROUPS[handle])
 
 
+def _stats_to_affine(stats: Tensor, handle: int, gamma: Tensor, beta: Tensor, eps: float, Co: int, mean, invstd,
+                     a, b, st) -> None:
+    """training-mode BatchNorm: (cross-rank SUM of ``stats`` under group ``handle``, then) the folded
+    affine.  With the peer exchange the all-reduce and the finalize are ONE kernel."""
+    peer = _PEER.get(handle) if handle else None
+    if peer is not None and stats.numel() <= peer.max_values:
+        _lib.call("ecb200_peer_allreduce_bn_finalize", _ptr(stats), Co, c_void_p(peer.bufs_dev), peer.rank,
+                  peer.world, _ptr(peer.seq), _ptr(gamma), _ptr(beta), float(eps), mean, invstd, a, b, st)
+        return
+    if handle:
+        dist.all_reduce(stats, group=_GROUPS[handle])
+    _lib.call("ecb200_bn_finalize", _ptr(stats), _ptr(gamma), _ptr(beta), None, None, 1, float(eps), Co, mean,
+              invstd, a, b, st)
+
+
+def _bstats_to_coeffs(bstats: Tensor, handle: int, count_ptr, a, invstd, Co: int, dgamma: Tensor, dbeta: Tensor,
+                      c1, c2, st) -> None:
+    """training-mode BatchNorm backward: local [sum g | sum g*xhat] -> dgamma, dbeta (local) and the
+    c1, c2 coefficients from the cross-rank sums; with the peer exchange in ONE kernel."""
+    peer = _PEER.get(handle) if handle else None
+    if handle:
+        bglobal = bstats.clone()
+        if peer is not None and bglobal.numel() <= peer.max_values:
+            _lib.call("ecb200_peer_allreduce_bwd_finalize", _ptr(bstats), _ptr(bglobal), Co, c_void_p(peer.bufs_dev),
+                      peer.rank, peer.world, _ptr(peer.seq), count_ptr, a, invstd, _ptr(dgamma), _ptr(dbeta),
+                      c1, c2, st)
+            return
+        dist.all_reduce(bglobal, group=_GROUPS[handle])
+    else:
+        bglobal = bstats
+    _lib.call("ecb200_bwd_finalize", _ptr(bstats), _ptr(bglobal), count_ptr, a, invstd, 1, Co, _ptr(dgamma),
+              _ptr(dbeta), c1, c2, st)
+
+
 def _ptr(t: Optional[Tensor]):
     return None if t is None else c_void_p(t.data_ptr())
 
@@ -294,13 +328,13 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
             _lib.call("ecb200_point_gemm", _ptr(x), _ptr(Wcat), B, C, N, 2 * Co, _ptr(Y), st)
         _lib.call("ecb200_edge_gather", _ptr(Y), _ptr(idx), _ptr(gamma_c), B, N, k, Co, _ptr(sel),
                   _ptr(arg), _ptr(esum), _ptr(stats) if use_batch_stats else None, st)
-        if use_batch_stats and group:
-            # the one exchange step of the path: [sum e, sum e^2, count] over the ranks
-            _allreduce_stats(stats, group)
-        _lib.call("ecb200_bn_finalize", _ptr(stats), _ptr(gamma_c), _ptr(beta_c),
-                  None if use_batch_stats else _ptr(running_mean),
-                  None if use_batch_stats else _ptr(running_var),
-                  int(use_batch_stats), float(eps), Co, mean, invstd, a, b, st)
+        if use_batch_stats:
+            # the one exchange step of the path: [sum e, sum e^2, count] over the ranks (group != 0),
+            # fused with the finalize when it runs over peer memory
+            _stats_to_affine(stats, group, gamma_c, beta_c, eps, Co, mean, invstd, a, b, st)
+        else:
+            _lib.call("ecb200_bn_finalize", None, _ptr(gamma_c), _ptr(beta_c), _ptr(running_mean),
+                      _ptr(running_var), 0, float(eps), Co, mean, invstd, a, b, st)
         _lib.call("ecb200_edge_apply", _ptr(sel), a, b, float(slope), B, N, Co, _ptr(out), _ptr(out_pm),
                   Co, st)
     if esum is None:
@@ -354,18 +388,16 @@ def edgeconv_bwd_op(gout: Optional[Tensor], gout_pm: Optional[Tensor], x: Tensor
         mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * Co * r) for r in range(4))
         _lib.call("ecb200_bwd_prep", _ptr(gout), _ptr(gout_pm), ld_pm, _ptr(sel), a, b, mean, invstd,
                   float(slope), B, N, Co, _ptr(g), _ptr(bstats), st)
-        if use_batch_stats and group:
-            bglobal = bstats.clone()
-            _allreduce_stats(bglobal, group)
-        else:
-            bglobal = bstats
         dgamma = torch.empty(Co, **f32)
         dbeta = torch.empty(Co, **f32)
         cc = torch.empty(2, Co, **f32)
         c1, c2 = c_void_p(cc.data_ptr()), c_void_p(cc.data_ptr() + 4 * Co)
-        _lib.call("ecb200_bwd_finalize", _ptr(bstats), _ptr(bglobal),
-                  c_void_p(stats.data_ptr() + 8 * 2 * Co), a, invstd,
-                  int(use_batch_stats), Co, _ptr(dgamma), _ptr(dbeta), c1, c2, st)
+        if use_batch_stats:
+            _bstats_to_coeffs(bstats, group, c_void_p(stats.data_ptr() + 8 * 2 * Co), a, invstd, Co, dgamma,
+                              dbeta, c1, c2, st)
+        else:
+            _lib.call("ecb200_bwd_finalize", _ptr(bstats), _ptr(bstats), None, a, invstd, 0, Co, _ptr(dgamma),
+                      _ptr(dbeta), c1, c2, st)
         rowptr = src = None
         if use_batch_stats:
             rowptr = torch.empty(M + 1, device=dev, dtype=torch.int32)
@@ -526,12 +558,10 @@ def embed_pool_fwd_op(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor,
         if use_batch_stats:
             if stats_in is None:
                 _lib.call("ecb200_colstats", _ptr(z), M, E, _ptr(stats), st)
-            if group:
-                _allreduce_stats(stats, group)
-        _lib.call("ecb200_bn_finalize", _ptr(stats), _ptr(gamma_c), _ptr(beta_c),
-                  None if use_batch_stats else _ptr(running_mean),
-                  None if use_batch_stats else _ptr(running_var),
-                  int(use_batch_stats), float(eps), E, mean, invstd, a, b, st)
+            _stats_to_affine(stats, group, gamma_c, beta_c, eps, E, mean, invstd, a, b, st)
+        else:
+            _lib.call("ecb200_bn_finalize", None, _ptr(gamma_c), _ptr(beta_c), _ptr(running_mean),
+                      _ptr(running_var), 0, float(eps), E, mean, invstd, a, b, st)
         _lib.call("ecb200_embed_pool", _ptr(z), a, b, float(slope), B, N, E, _ptr(pooled), _ptr(arg), st)
     return [pooled, arg, affine, stats]
 
@@ -557,17 +587,16 @@ def embed_pool_bwd_op(gpool: Tensor, z: Tensor, arg: Tensor, affine: Tensor, sta
         bstats = torch.zeros(2 * E, device=dev, dtype=torch.float64)
         _lib.call("ecb200_embed_pool_bwd_stats", _ptr(z), _ptr(gpool), _ptr(arg), a, b, mean, invstd,
                   float(slope), B, N, E, _ptr(bstats), st)
-        if use_batch_stats and group:
-            bglobal = bstats.clone()
-            _allreduce_stats(bglobal, group)
-        else:
-            bglobal = bstats
         dgamma = torch.empty(E, **f32)
         dbeta = torch.empty(E, **f32)
         cc = torch.empty(2, E, **f32)
         c1, c2 = c_void_p(cc.data_ptr()), c_void_p(cc.data_ptr() + 4 * E)
-        _lib.call("ecb200_bwd_finalize", _ptr(bstats), _ptr(bglobal), c_void_p(stats.data_ptr() + 8 * 2 * E),
-                  a, invstd, int(use_batch_stats), E, _ptr(dgamma), _ptr(dbeta), c1, c2, st)
+        if use_batch_stats:
+            _bstats_to_coeffs(bstats, group, c_void_p(stats.data_ptr() + 8 * 2 * E), a, invstd, E, dgamma, dbeta,
+                              c1, c2, st)
+        else:
+            _lib.call("ecb200_bwd_finalize", _ptr(bstats), _ptr(bstats), None, a, invstd, 0, E, _ptr(dgamma),
+                      _ptr(dbeta), c1, c2, st)
         dz = torch.empty(M, E, **f32)
         _lib.call("ecb200_embed_pool_bwd_dz", _ptr(z), _ptr(gpool), _ptr(arg), a, b, mean, c1, c2,
                   float(slope), B, N, E, _ptr(dz), st)

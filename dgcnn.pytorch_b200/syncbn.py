@@ -32,11 +32,8 @@ class _SyncBNRows(torch.autograd.Function):
             affine = torch.empty(4, F, device=dev, dtype=torch.float32)
             mean, invstd, a, b = (c_void_p(affine.data_ptr() + 4 * F * r) for r in range(4))
             _lib.call("ecb200_colstats", ops._ptr(x), M, F, ops._ptr(stats), st)
-            if group:
-                ops._allreduce_stats(stats, group)
             g32, b32 = gamma.detach().contiguous().float(), beta.detach().contiguous().float()
-            _lib.call("ecb200_bn_finalize", ops._ptr(stats), ops._ptr(g32), ops._ptr(b32), None, None, 1,
-                      float(eps), F, mean, invstd, a, b, st)
+            ops._stats_to_affine(stats, group, g32, b32, eps, F, mean, invstd, a, b, st)   # exchange + finalize
             if running_mean is not None:
                 _lib.call("ecb200_bn_update_running", ops._ptr(stats), F, float(momentum), ops._ptr(running_mean),
                           ops._ptr(running_var), ops._ptr(nbt), st)

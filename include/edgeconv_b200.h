@@ -271,6 +271,20 @@ size_t ecb200_peer_buffer_bytes(int world);
 int ecb200_peer_allreduce(double* vals, int n, void* const* peer_bufs, int rank, int world,
                           unsigned long long* seq_counter, void* stream);
 
+/* The exchange fused with the per-channel step that consumes it (one launch instead of two):
+ *   ..._bn_finalize : stats[2Co+1] all-reduced in place, then exactly ecb200_bn_finalize(training)
+ *   ..._bwd_finalize: bstats_global[2Co] (a copy of bstats_local) all-reduced in place, then exactly
+ *                     ecb200_bwd_finalize(training) */
+int ecb200_peer_allreduce_bn_finalize(double* stats, int Co, void* const* peer_bufs, int rank, int world,
+                                      unsigned long long* seq_counter, const float* gamma,
+                                      const float* beta, float eps, float* mean, float* invstd, float* a,
+                                      float* b, void* stream);
+int ecb200_peer_allreduce_bwd_finalize(const double* bstats_local, double* bstats_global, int Co,
+                                       void* const* peer_bufs, int rank, int world,
+                                       unsigned long long* seq_counter, const double* count_dev,
+                                       const float* a, const float* invstd, float* dgamma, float* dbeta,
+                                       float* c1, float* c2, void* stream);
+
 /* conv5 of the backbone (models/dgcnn.py:74-78 applied at :102) as a per-point GEMM on the tensor cores
  * with its BatchNorm statistics in the epilogue: Z[M,E] = X[M,K] . W[E,K]^T (X = the channels-last
  * 512-channel concat of dgcnn.py:100), stats[2E+1] (fp64, zeroed by the caller; may be NULL) +=

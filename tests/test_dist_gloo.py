@@ -128,13 +128,21 @@ def _grad_sync_worker(rank, world, port, out):
     sync = ecd.FlatGradSync(params)
     assert not sync.overlap                                  # CPU: no side stream, one flat all-reduce
     assert sync.flat_late.numel() == 12 * 6 and sync.flat_early.numel() == 3 * 6
-    # every .grad is a view into the flat buffer, late bucket first
+    # a step starts with every .grad None: autograd stores its gradients, nothing accumulates in place
+    sync.zero()
+    assert all(p.grad is None for p in params)
+    loss = sum(((rank + 1.0) * (i + 1) * p).sum() for i, p in enumerate(params[:-1]))   # the last one gets no gradient
+    loss.backward()                                          # d/dp = (rank+1)*(i+1)
+    sync.average()
+    # afterwards every .grad is its slice of the flat buffer, late bucket first
     assert params[0].grad.data_ptr() == sync.flat.data_ptr()
+    assert params[3].grad.data_ptr() == sync.flat.data_ptr() + 3 * 6 * 4
     assert params[12].grad.data_ptr() == sync.flat_early.data_ptr()
+    assert torch.equal(params[-1].grad, torch.zeros(3, 2))   # no gradient this step -> zeros, not stale values
+    # a second step reuses the buffer
     sync.zero()
     loss = sum(((rank + 1.0) * (i + 1) * p).sum() for i, p in enumerate(params))
-    loss.backward()                                          # d/dp = (rank+1)*(i+1), accumulated in place
-    assert params[3].grad.data_ptr() == sync.flat.data_ptr() + 3 * 6 * 4
+    loss.backward()
     sync.average()
     torch.save([p.grad.clone() for p in params], f"{out}.{rank}")
     dist.destroy_process_group()
