@@ -102,7 +102,10 @@ def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
         if idx is None:
             idx = ops.knn_tc_op(xhi, xlo, xx, B, N, int(k))
     if idx is None:
-        idx = ops.knn_cached(x.detach().contiguous(), int(k), False)   # order over k is irrelevant here
+        # the order over k is irrelevant here, but the xyz graph is asked for again by the callers of
+        # knn() / get_graph_feature() on the same tensor (model_partseg.py:26, layers.py:45), which
+        # need it nearest-first: compute it sorted once and let them reuse it
+        idx = ops.knn_cached(x.detach().contiguous(), int(k), C <= 16)
     group = _sync_group(bn)
     slope = float(getattr(act, "negative_slope", 0.0))
     out = ops.edgeconv(x, idx, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,

@@ -619,12 +619,13 @@ def _ep_setup(ctx, inputs, output):
 
 def _ep_backward(ctx, grads):
     gpool = grads[0]
+    n_in = len(ctx.needs_input_grad)      # 11 or 12: a defaulted trailing stats_in may not be part of the call
     if gpool is None:
-        return (None,) * 12
+        return (None,) * n_in
     z, arg, affine, stats = ctx.saved_tensors
     B, N, use_batch_stats, slope, group = ctx.cfg
     dz, dgamma, dbeta = embed_pool_bwd_op(gpool, z, arg, affine, stats, B, N, use_batch_stats, slope, group)
-    return (dz, None, None, dgamma, dbeta) + (None,) * 7
+    return (dz, None, None, dgamma, dbeta) + (None,) * (n_in - 5)
 
 
 embed_pool_fwd_op.register_autograd(_ep_backward, setup_context=_ep_setup)

@@ -475,7 +475,9 @@ def test_dgcnn_cls_pooled_path_equals_unfused(ec):
         if gb[n].abs().max().item() < 1e-5:       # biases feeding a BatchNorm: gradient is 0 up to rounding
             assert ga[n].abs().max().item() < 1e-5, n
             continue
-        assert_rel(ga[n], gb[n], rel=2e-4, what=f"grad {n}")
+        # conv5 runs as the own 3xTF32 GEMM in one path and as the library's fp32 convolution in the
+        # other: the ~1e-6 forward difference can move a tied max / a LeakyReLU at its kink
+        assert_rel(ga[n], gb[n], rel=5e-4, what=f"grad {n}")
     for k in sa:
         if sa[k].dtype.is_floating_point:
             assert_rel(sa[k], sb[k], rel=1e-5, what=f"buffer {k}")
