@@ -46,10 +46,11 @@ import torch  # noqa: E402
 
 METRIC = "DGCNN-cls fwd+bwd clouds/sec (N=1024,k=20)"
 UNIT = "clouds/s"
-CONV5_NOTE = ("conv5 forward = own tcgen05 GEMM (ecb200_embed_gemm) on the channels-last concat with the BatchNorm "
-              "statistics in its epilogue, plain TF32 on fp32 operands because torch.backends.cudnn.allow_tf32 is "
-              "on (PyTorch default; 3xTF32 when it is off); conv5 backward = library convolution backward (TF32); "
-              "BatchNorm + LeakyReLU + max|avg pooling in own kernels (embed_pool); 3 head linears in torch")
+CONV5_NOTE = ("conv5 GEMM: library convolution (cuDNN, TF32 -- torch.backends.cudnn.allow_tf32 is on, PyTorch's default) on the "
+              "channels-last concat; an own tcgen05 GEMM with the BatchNorm statistics in its epilogue exists "
+              "(ecb200_embed_gemm: 3xTF32 whenever allow_tf32 is off, TF32 by ECB200_CONV5=tf32) but its 128x128 tiles "
+              "are 2.9x slower than the library's 2-SM 256x256 kernel; BatchNorm + LeakyReLU + max|avg pooling in own "
+              "kernels (embed_pool); 3 head linears in torch")
 
 
 def parse():

@@ -67,7 +67,11 @@ struct EpiDw {  // D[o, c] += into dWcat[o, c]
 // `three` = 1: D += Ahi.Bhi + Ahi.Blo + Alo.Bhi (3xTF32, fp32-equivalent); 0: D += A.B in plain TF32 from
 // the `hi` maps only (which may then be the raw fp32 arrays: the tensor core reads their top 19 bits).
 // blockIdx.z = tile of BN output columns (rows [z*BN, +BN) of B).
-template <bool MN_MAJOR, class Epi>
+// C22: thread-block clusters of 2 x 2 output tiles (cluster dims (2,1,2), K-major operands, BN = 128): the
+// two CTAs of a row pair share their B tile and the two of a column pair their A tile, so every CTA
+// fetches HALF of each and TMA multicasts it to its partner -- the L2 -> SM operand traffic, which
+// bounds a 128 x 128 fp32 tile at K = 512, is halved.
+template <bool MN_MAJOR, class Epi, bool C22 = false>
 __global__ void __launch_bounds__(NT, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__ CUtensorMap a_lo,
                const __grid_constant__ CUtensorMap b_hi, const __grid_constant__ CUtensorMap b_lo,
@@ -82,16 +86,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
   const long long k_end = k_beg + kslab < K ? k_beg + kslab : K;
   const int nkb = (int)((k_end - k_beg + KB - 1) / KB);
 
+  uint32_t cx = 0, cz = 0;
+  uint16_t amask = 0, bmask = 0, emask = 0;
+  if (C22) {
+    const uint32_t crank = cluster_ctarank();          // = x + 2 z inside the (2,1,2) cluster
+    cx = crank & 1u; cz = crank >> 1;
+    amask = (uint16_t)((1u << cx) | (1u << (cx + 2)));  // same row tile, both column tiles: share A
+    bmask = (uint16_t)(3u << (2 * cz));                 // same column tile, both row tiles: share B
+    emask = (uint16_t)(amask | bmask);                  // everyone whose multicasts land in my stages
+  }
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&a_hi); prefetch_tensormap(&a_lo);
     prefetch_tensormap(&b_hi); prefetch_tensormap(&b_lo);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&T->full[s], 1); mbar_init(&T->empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&T->full[s], 1); mbar_init(&T->empty[s], C22 ? 3 : 1); }
     mbar_init(&T->done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&T->tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (C22) cluster_sync_all();   // the partners' barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = T->tmem_slot;
   const uint32_t b_bytes = (uint32_t)(BN * KB * 4);  // one half of the B stage
@@ -107,7 +121,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
         unsigned char* st = base + (size_t)stage * 4 * SUB;  // [A hi | A lo | B hi | B lo]
         mbar_expect_tx(&T->full[stage], three ? 2 * SUB + 2 * b_bytes : SUB + b_bytes);
         const int k0 = (int)(k_beg + (long long)kb * KB);
-        if (!MN_MAJOR) {
+        if (C22) {
+          // my half of the A tile (64 rows) to both CTAs of my row pair... of my column pair, and my
+          // half of the B tile to both CTAs of my row pair; maps carry 64-row boxes
+          constexpr int HALF = SUB / 2;
+          tma_load_2d_mc(st + cz * HALF, &a_hi, &T->full[stage], k0, mt * BM + (int)cz * 64, amask);
+          tma_load_2d_mc(st + 2 * SUB + cx * HALF, &b_hi, &T->full[stage], k0, brow + (int)cx * 64, bmask);
+          if (three) {
+            tma_load_2d_mc(st + SUB + cz * HALF, &a_lo, &T->full[stage], k0, mt * BM + (int)cz * 64, amask);
+            tma_load_2d_mc(st + 3 * SUB + cx * HALF, &b_lo, &T->full[stage], k0, brow + (int)cx * 64, bmask);
+          }
+        } else if (!MN_MAJOR) {
           tma_load_2d(st, &a_hi, &T->full[stage], k0, mt * BM);
           tma_load_2d(st + 2 * SUB, &b_hi, &T->full[stage], k0, brow);
           if (three) {
@@ -162,7 +186,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
             mma_tf32(tmem_d, dal, dbh, idesc, 1);
           }
         }
-        mma_commit(&T->empty[stage]);
+        if (C22) mma_commit_mc(&T->empty[stage], emask);
+        else     mma_commit(&T->empty[stage]);
         if (kb + 1 == nkb) mma_commit(&T->done);
       }
       __syncwarp();
@@ -202,6 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap a_hi, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (C22) cluster_sync_all();   // no CTA exits while a partner can still signal its barriers
 }
 
 struct EpiDxImpl : EpiDx {
@@ -387,19 +413,45 @@ extern "C" int ecb200_embed_gemm(const float* xhi, const float* xlo, const float
   ECB_REQUIRE(M >= 1 && K >= KB && K % KB == 0 && E >= 128 && E % 128 == 0,
               "ecb200_embed_gemm: needs K a multiple of 32 and E a multiple of 128 (K=%d E=%d)", K, E);
   const int three = xlo != nullptr;
-  CUtensorMap ah, al, bh, bl;
-  int rc;
-  if ((rc = make_map(&ah, xhi, M, K, KB, BM))) return rc;
-  if ((rc = make_map(&al, three ? xlo : xhi, M, K, KB, BM))) return rc;
-  if ((rc = make_map(&bh, whi, E, K, KB, 128))) return rc;
-  if ((rc = make_map(&bl, three ? wlo : whi, E, K, KB, 128))) return rc;
-  auto kern = gemm_tc_kernel<false, EpiRowStats>;
-  static thread_local bool seen[ecb200::kMaxDevices] = {};
-  if ((rc = opt_in_smem(kern, seen))) return rc;
   EpiRowStats epi;
   epi.Z = Z; epi.M = M; epi.ldz = E; epi.stats = stats; epi.E = E;
   dim3 grid((unsigned)ecb200::ceil_div64(M, BM), 1, (unsigned)(E / 128));
-  kern<<<grid, NT, SMEM_BYTES, (cudaStream_t)stream>>>(ah, al, bh, bl, 128, (long long)K, (long long)K, three, epi);
-  ECB_LAUNCH_CHECK("gemm_tc_kernel<embed>");
+  const bool c22 = grid.x % 2 == 0 && grid.z % 2 == 0;   // 2 x 2 clusters need even tile counts
+  const int box = c22 ? 64 : 128;
+  CUtensorMap ah, al, bh, bl;
+  int rc;
+  if ((rc = make_map(&ah, xhi, M, K, KB, box))) return rc;
+  if ((rc = make_map(&al, three ? xlo : xhi, M, K, KB, box))) return rc;
+  if ((rc = make_map(&bh, whi, E, K, KB, box))) return rc;
+  if ((rc = make_map(&bl, three ? wlo : whi, E, K, KB, box))) return rc;
+  if (!c22) {
+    auto kern = gemm_tc_kernel<false, EpiRowStats, false>;
+    static thread_local bool seen[ecb200::kMaxDevices] = {};
+    if ((rc = opt_in_smem(kern, seen))) return rc;
+    kern<<<grid, NT, SMEM_BYTES, (cudaStream_t)stream>>>(ah, al, bh, bl, 128, (long long)K, (long long)K, three, epi);
+    ECB_LAUNCH_CHECK("gemm_tc_kernel<embed>");
+    return ECB200_OK;
+  }
+  auto kern = gemm_tc_kernel<false, EpiRowStats, true>;
+  static thread_local bool seen2[ecb200::kMaxDevices] = {};
+  if ((rc = opt_in_smem(kern, seen2))) return rc;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 2;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, 128, (long long)K, (long long)K, three, epi);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    ecb200::set_error("launch of gemm_tc_kernel<embed, 2x2 cluster> failed: %s", cudaGetErrorString(e));
+    return ECB200_ERR_CUDA;
+  }
   return ECB200_OK;
 }

@@ -650,16 +650,19 @@ def embed_pool(z: Tensor, B: int, N: int, gamma: Tensor, beta: Tensor, running_m
 
 # ------------------------------------------------ conv5 as a per-point GEMM with BN statistics
 def embed_gemm_mode(K: int, E: int) -> str:
-    """How conv5's GEMM runs: "tf32" (own tcgen05 kernel, plain TF32 on the raw fp32 operands -- the
-    precision class of the library convolution under torch.backends.cudnn.allow_tf32, PyTorch's
-    default), "3xtf32" (own kernel, fp32-equivalent; chosen when allow_tf32 is off) or "cudnn"
-    (library convolution: unsupported shape, or ECB200_CONV5=cudnn)."""
+    """How conv5's GEMM runs: "cudnn" (library convolution), "tf32" (own tcgen05 kernel, plain TF32
+    on the raw fp32 operands, statistics in the epilogue) or "3xtf32" (own kernel, fp32-equivalent).
+    auto (default): the library convolution while torch.backends.cudnn.allow_tf32 is on (PyTorch's
+    default: its 2-SM 256x256 TF32 kernel runs at the L2-bandwidth bound of this fp32-operand GEMM,
+    67 us at M=32768, vs 240 us for the own 128x128-tile kernel -- profiles/r2_embed_gemm.txt), the
+    own 3xTF32 kernel when it is off (fp32 semantics asked for: 359 us incl. the operand split, where
+    the library falls back to an FP32 SIMT convolution).  ECB200_CONV5=cudnn|tf32|3xtf32 overrides."""
     mode = os.environ.get("ECB200_CONV5", "auto")
     if mode == "cudnn" or K % 32 != 0 or E % 128 != 0:
         return "cudnn"
     if mode in ("tf32", "3xtf32"):
         return mode
-    return "tf32" if torch.backends.cudnn.allow_tf32 else "3xtf32"
+    return "cudnn" if torch.backends.cudnn.allow_tf32 else "3xtf32"
 
 
 @torch.library.custom_op("edgeconv_b200::embed_gemm", mutates_args=(), device_types="cuda")
