@@ -310,7 +310,8 @@ def gather_kernel_bytes(M, k, Co, training=True):
 
 
 # forward kernels of the EdgeConv path (kNN + edge MLP + max), by name fragments of the kernels
-EDGE_FWD_KERNELS = ("knn_tc_kernel<32, false", "knn_xyz_kernel", "knn_fma_kernel", "sqnorms_kernel", "split_tf32_kernel",
+EDGE_FWD_KERNELS = ("knn_tc_kernel<32, false", "knn_tc_kernel<32, 0", "knn_xyz_kernel", "knn_fma_kernel", "sqnorms_kernel",
+                    "split_tf32_kernel", "split_f16_kernel", "pack_xyz_f16_kernel", "absmax_kernel",
                     "prepare_weights_kernel", "pack_weight_kernel", "gemm_tile_kernel", "knn_tc_kernel<32, true", "edge_gather_kernel",
                     "bn_finalize_kernel", "edge_apply_kernel", "bn_update_running_kernel")
 
@@ -555,15 +556,39 @@ def run_b200(a):
     # layer (norm terms and the error-compensation MMAs do not count)
     roof = None
     knn_flops = sum(2.0 * M * N * c for c, _ in layers if c % 32 == 0 and 32 <= c <= 128)
-    t_us = kernel_us("knn_tc_kernel<32, false") or kernel_us("knn_tc_kernel<32, 0")
+    f16x3_peak = pk["bf16_tflops"] / 3.0
+
+    def knn_tc_us(xyz):
+        """kNN tensor-core kernels of the graph profile: template tail '<.., F16, TERMS>'; TERMS == 1 is
+        the xyz layer (one MMA per tile), TERMS == 3 the feature-space layers."""
+        if not kprof:
+            return None, None
+        t, f16 = 0.0, False
+        for n, v in kprof.items():
+            if not (n.startswith("knn_tc_kernel<32, false") or n.startswith("knn_tc_kernel<32, 0")):
+                continue
+            tail = n.rstrip(">").split(",")[-2:]
+            is_xyz = len(n.split(",")) >= 6 and tail[-1].strip() == "1"
+            if is_xyz != xyz:
+                continue
+            t += v["us_per_step"]
+            f16 = f16 or (len(n.split(",")) >= 6 and tail[0].strip() in ("true", "1"))
+        return (t or None), f16
+    t_us, knn_f16 = knn_tc_us(False)
     src = "in-graph (CUPTI)"
-    if not t_us and entry_ms("ecb200_knn_tc"):
-        t_us, src = entry_ms("ecb200_knn_tc") * 1e3, "eager CUDA-event brackets"
+    if not t_us and (entry_ms("ecb200_knn_tc_f16") or entry_ms("ecb200_knn_tc")):
+        knn_f16 = bool(entry_ms("ecb200_knn_tc_f16"))
+        t_us, src = (entry_ms("ecb200_knn_tc_f16") or entry_ms("ecb200_knn_tc")) * 1e3, "eager CUDA-event brackets"
     if t_us:
         ach = knn_flops / (t_us * 1e-6) / 1e12
-        roof = {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": ach, "peak": tf32x3_peak,
-                "unit": "TFLOP/s", "frac": ach / tf32x3_peak, "traffic": None,
-                "peak_source": pk["source"] + " bf16 burst / 2 (tf32) / 3 (3xTF32)",
+        peak = f16x3_peak if knn_f16 else tf32x3_peak
+        roof = {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "operands": ("packed fp16 hi/lo halves (kind::f16, 3 MMAs per product: same 11-bit significands and "
+                             "error bound as 3xTF32 at twice the pipe rate)") if knn_f16 else "tf32 hi/lo halves (3xTF32)",
+                "peak_source": pk["source"] + (" bf16/fp16 burst / 3 (three MMAs per product)" if knn_f16
+                                               else " bf16 burst / 2 (tf32) / 3 (3xTF32)"),
+                "frac_of_3xtf32_roofline": ach / tf32x3_peak,
                 "launches_per_step": 3, "flops_per_step": knn_flops, "us_per_step": t_us, "timing": src}
     # roofline 2: the neighbour gather against HBM (SURVEY's Q_edge and the kernel's own byte count)
     roof_gather = None
@@ -592,14 +617,19 @@ def run_b200(a):
                        "us_per_step": t_us, "timing": src}
     # roofline 3: xyz kNN against the FP32 FMA issue peak (3 FMAs per pair, one sweep is algorithmic)
     roof_xyz = None
+    xyz_kernel = "knn_xyz_kernel"
     t_us = kernel_us("knn_xyz_kernel")
+    if not t_us and knn_tc_us(True)[0]:
+        t_us, xyz_kernel = knn_tc_us(True)[0], "knn_tc_kernel<.., F16, TERMS = 1> (one kind::f16 MMA per 128x128 tile and sweep)"
+    if not t_us and entry_ms("ecb200_knn_tc_xyz"):
+        t_us, xyz_kernel = entry_ms("ecb200_knn_tc_xyz") * 1e3, "ecb200_knn_tc_xyz (eager brackets)"
     if not t_us and entry_ms("ecb200_knn"):
         t_us = entry_ms("ecb200_knn") * 1e3
     sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
     fma_peak = 148 * 128 * sm_mhz * 1e6          # FMA/s
     if t_us:
         pairs = float(M) * N
-        roof_xyz = {"bound": "fp32-fma issue", "kernel": "knn_xyz_kernel", "pairs_per_s": pairs / (t_us * 1e-6),
+        roof_xyz = {"bound": "fp32-fma issue", "kernel": xyz_kernel, "pairs_per_s": pairs / (t_us * 1e-6),
                     "fma_per_pair_algorithmic": 3, "frac_of_fma_peak": 3 * pairs / (t_us * 1e-6) / fma_peak,
                     "fma_peak_per_s": fma_peak, "us_per_step": t_us}
     # roofline 4: the whole fused EdgeConv forward (kNN + edge MLP + max, 4 layers) against its

@@ -22,6 +22,12 @@ SIGNATURES = {
     "ecb200_split_tf32": (P, I, I, I, P, P, P, P),
     "ecb200_knn_tc": (P, P, P, I, I, I, I, I, P, P, Z, P),
     "ecb200_debug_tc_scores": (P, P, P, I, I, I, P, P),
+    "ecb200_absmax": (P, LL, P, P),
+    "ecb200_split_f16": (P, I, I, I, P, P, P, P, P, P, P, P),
+    "ecb200_knn_tc_f16": (P, P, P, I, I, I, I, P, P, P),
+    "ecb200_pack_xyz_f16": (P, I, I, I, P, P, P, P),
+    "ecb200_knn_tc_xyz": (P, P, P, I, I, I, P, P, P),
+    "ecb200_debug_tc_scores_f16": (P, P, P, I, I, I, P, P),
     "ecb200_debug_tc_timeline": (P, P, P, I, I, I, I, P, P, P, P),
     "ecb200_split_rows_tf32": (P, LL, P, P, P),
     "ecb200_point_gemm_tc": (P, P, P, P, LL, I, I, P, P),
@@ -34,6 +40,7 @@ SIGNATURES = {
     "ecb200_bn_finalize": (P, P, P, P, P, I, F, I, P, P, P, P, P),
     "ecb200_bn_update_running": (P, I, F, P, P, P, P),
     "ecb200_edge_apply": (P, P, P, F, I, I, I, P, P, LL, P),
+    "ecb200_edge_apply_amax": (P, P, P, F, I, I, I, P, P, LL, P, P),
     "ecb200_bwd_prep": (P, P, LL, P, P, P, P, P, F, I, I, I, P, P, P),
     "ecb200_bwd_finalize": (P, P, P, P, P, I, I, P, P, P, P, P),
     "ecb200_reverse_graph": (P, I, I, I, P, P, P, P),

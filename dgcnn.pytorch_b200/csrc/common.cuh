@@ -65,6 +65,23 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// max over the block (any shape up to 1024 threads); the result is valid in thread 0
+__device__ __forceinline__ unsigned block_max_u32(unsigned m) {
+  __shared__ unsigned wm[32];
+  const int t = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const int nw = (blockDim.x * blockDim.y * blockDim.z + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((t & 31) == 0) wm[t >> 5] = m;
+  __syncthreads();
+  if (t < 32) {
+    m = t < nw ? wm[t] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  return m;
+}
+
 __device__ __forceinline__ float leaky(float y, float slope) { return y > 0.f ? y : y * slope; }
 
 // round to tf32 (nearest, ties away): hi = tf32_rna(v), lo = tf32_rna(v - hi) is the operand pair of

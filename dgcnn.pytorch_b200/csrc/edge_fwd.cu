@@ -156,8 +156,10 @@ __global__ void bn_update_running_kernel(const double* __restrict__ stats, int C
 __global__ void __launch_bounds__(256)
 edge_apply_kernel(const float* __restrict__ sel, const float* __restrict__ a,
                   const float* __restrict__ b, float slope, int N, int Co,
-                  float* __restrict__ out, float* __restrict__ out_pm, long long ld_pm) {
+                  float* __restrict__ out, float* __restrict__ out_pm, long long ld_pm,
+                  unsigned* __restrict__ amax) {
   __shared__ float tile[32][33];
+  unsigned mx = 0u;   // max |y| of this thread as a bit pattern (non-negative floats order like unsigned)
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int n0 = blockIdx.x * 32, o0 = blockIdx.y * 32, bb = blockIdx.z;
   const int o = o0 + tx;
@@ -170,8 +172,16 @@ edge_apply_kernel(const float* __restrict__ sel, const float* __restrict__ a,
       const size_t m = (size_t)bb * N + n;
       y = ecb200::leaky(fmaf(ao, sel[m * Co + o], bo), slope);
       if (out_pm) out_pm[m * ld_pm + o] = y;
+      mx = max(mx, __float_as_uint(fabsf(y)));
     }
     tile[p][tx] = y;
+  }
+  if (amax) {
+    // the next layer's operand scale (ecb200_split_f16): one monotone atomic per block into one of
+    // ECB200_AMAX_SLOTS slots, skipped once the slot is already as large
+    mx = ecb200::block_max_u32(mx);
+    unsigned* slot = amax + ((blockIdx.x + 3 * blockIdx.y + 5 * blockIdx.z) & (ECB200_AMAX_SLOTS - 1));
+    if (tx == 0 && ty == 0 && mx > *reinterpret_cast<volatile unsigned*>(slot)) atomicMax(slot, mx);
   }
   if (!out) return;
   __syncthreads();
@@ -313,15 +323,25 @@ extern "C" int ecb200_bn_update_running(const double* stats, int Co, float momen
   return ECB200_OK;
 }
 
+extern "C" int ecb200_edge_apply_amax(const float* sel, const float* a, const float* b, float slope,
+                                      int B, int N, int Co, float* out, float* out_pm, long long ld_pm,
+                                      float* amax, void* stream);
 extern "C" int ecb200_edge_apply(const float* sel, const float* a, const float* b, float slope,
                                  int B, int N, int Co, float* out, float* out_pm, long long ld_pm,
                                  void* stream) {
+  return ecb200_edge_apply_amax(sel, a, b, slope, B, N, Co, out, out_pm, ld_pm, nullptr, stream);
+}
+
+extern "C" int ecb200_edge_apply_amax(const float* sel, const float* a, const float* b, float slope,
+                                      int B, int N, int Co, float* out, float* out_pm, long long ld_pm,
+                                      float* amax, void* stream) {
   ECB_REQUIRE(sel && a && b && (out || out_pm), "ecb200_edge_apply: null pointer");
   ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1 && Co >= 1, "ecb200_edge_apply: bad shape");
   ECB_REQUIRE(!out_pm || ld_pm >= Co, "ecb200_edge_apply: ld_pm=%lld smaller than Co=%d", ld_pm, Co);
   dim3 grid(ecb200::ceil_div(N, 32), ecb200::ceil_div(Co, 32), B);
+  if (amax) ECB_CUDA(cudaMemsetAsync(amax, 0, ECB200_AMAX_SLOTS * sizeof(float), (cudaStream_t)stream));
   edge_apply_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(sel, a, b, slope, N, Co, out, out_pm,
-                                                                    ld_pm);
+                                                                    ld_pm, reinterpret_cast<unsigned*>(amax));
   ECB_LAUNCH_CHECK("edge_apply_kernel");
   return ECB200_OK;
 }

@@ -14,6 +14,7 @@
 // The query tile (A) stays resident in shared memory; candidate tiles (B) stream through a
 // TMA / mbarrier ring.  Pass A and pass B of the selector are two sweeps of the same MMAs.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include <stdlib.h>
@@ -118,11 +119,20 @@ __device__ __noinline__ float shrink_survivors(uint64_t* buf, int cnt, int k) {
 //               same candidate tiles: each CTA fetches 1/CL of every tile and TMA multicasts it to
 //               all of them, so the L2 -> SM traffic of the candidates drops by CL.
 // S:            ring stages of 32 KB.
-template <int NBINS, bool DEBUG, int CL, int S>
+// F16:          the operands are packed FP16 pairs (two channels per 32-bit word; values scaled by a
+//               power of two into FP16's range by ecb200_split_f16) and the MMAs are kind::f16: the
+//               same 11-bit significands as tf32 at twice the rate.  In words nothing else changes:
+//               `nkb` counts blocks of 32 WORDS (64 channels) then.
+// TERMS:        3 = error-compensated product hi.hi + hi.lo + lo.hi (pass A ranks with hi.hi alone);
+//               1 = the hi arrays already carry the whole product (xyz layer: the three terms of a
+//               3-channel point sit side by side in ONE 16-deep K step), both passes issue the same
+//               single MMA and no margin is needed.
+// ksteps:       K steps per 32-word block that hold data (4; 1 for the packed xyz operands).
+template <int NBINS, bool DEBUG, int CL, int S, bool F16 = false, int TERMS = 3>
 __global__ void __launch_bounds__(NT, 1)
 knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g,
               const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-              const float* __restrict__ xx, int Na, int N, int nkb, int k, int cap,
+              const float* __restrict__ xx, int Na, int N, int nkb, int ksteps, int k, int cap,
               int32_t* __restrict__ idx, float* __restrict__ dbg, long long* tl) {
   // A operand: rows [b*Na + rt*128, +128) of a_hi_g / a_lo_g [*, C] (the queries; for the GEMM use
   // the points), copied ONCE into tensor memory (lane = row, column = channel): the MMAs then
@@ -198,6 +208,7 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
         else        tma_load_2d(dst, m, bar, c0, r0);
       };
       if (!DEBUG) {
+        for (int sweep = 0; sweep < (TERMS == 1 ? 2 : 1); ++sweep)
         for (int ct = 0; ct < nct; ++ct)
           for (int kb = 0; kb < nkb; kb += kpa, ++n) {
             mbar_wait(&T->b_empty[stage], phase ^ 1);
@@ -212,6 +223,7 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
       }
+      if (TERMS == 3)
       for (int ct = 0; ct < nct; ++ct)
         for (int kb = 0; kb < nkb; ++kb, ++n) {
           mbar_wait(&T->b_empty[stage], phase ^ 1);
@@ -229,7 +241,11 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp in the loop, one elected lane issues) ========
     {
-      const uint32_t idesc = make_idesc_tf32(BM, BN);
+      const uint32_t idesc = F16 ? make_idesc_f16(BM, BN) : make_idesc_tf32(BM, BN);
+      auto mma = [&](uint32_t d, uint32_t a, uint32_t bdesc, uint32_t acc) {
+        if (F16) mma_f16_ts_lo(d, a, bdesc, idesc, acc);
+        else     mma_tf32_ts_lo(d, a, bdesc, idesc, acc);
+      };
       const uint32_t tmem_base = __shfl_sync(0xffffffffu, T->tmem_slot, 0);   // warp-uniform by construction
       mbar_wait(&T->a_full, 0);
       tc_fence_after();
@@ -244,7 +260,9 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
         else        mma_commit(&T->b_empty[st]);
       };
       if (!DEBUG) {
-        // pass A: plain TF32 on the hi halves (ranked with an error margin), two K-blocks per stage
+        // pass A: one product of the hi halves (ranked with an error margin), two K-blocks per stage;
+        // with TERMS == 1 the second sweep is the same again
+        for (int sweep = 0; sweep < (TERMS == 1 ? 2 : 1); ++sweep)
         for (int ct = 0; ct < nct; ++ct, ++tile) {
           const int as = tile & 1;  // stage g is consumed by epilogue warpgroup g
           mbar_wait(&T->t_empty[as], ((tile >> 1) & 1) ^ 1);  // that group drained this stage
@@ -260,7 +278,8 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
                 const uint32_t ah = a_col + (uint32_t)((kb + j) * KB);
 #pragma unroll
                 for (int k8 = 0; k8 < KB / UMMA_K; ++k8)
-                  mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + j * LO_STEP + k8 * K8_STEP, idesc, (kb | j | k8) != 0);
+                  if (k8 < ksteps)
+                    mma(d_tmem, ah + k8 * UMMA_K, bh + j * LO_STEP + k8 * K8_STEP, (kb | j | k8) != 0);
               }
               release(stage);
               if (kb + kpa >= nkb) mma_commit(&T->t_full[as]);  // accumulator ready for the epilogue
@@ -271,7 +290,8 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
           ECB_STAMP(1, 2 * tile + 1);
         }
       }
-      // pass B (and the only sweep of the dense-store variant): 3xTF32, hi.hi + hi.lo + lo.hi
+      // pass B (and the only sweep of the dense-store variant): three terms, hi.hi + hi.lo + lo.hi
+      if (TERMS == 3)
       for (int ct = 0; ct < nct; ++ct, ++tile) {
         const int as = tile & 1;
         mbar_wait(&T->t_empty[as], ((tile >> 1) & 1) ^ 1);
@@ -286,9 +306,9 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
           if (elect_one_sync()) {
 #pragma unroll
             for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
-              mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, (kb | k8) != 0);
-              mma_tf32_ts_lo(d_tmem, ah + k8 * UMMA_K, bh + LO_STEP + k8 * K8_STEP, idesc, 1);
-              mma_tf32_ts_lo(d_tmem, ah + (uint32_t)C + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, 1);
+              mma(d_tmem, ah + k8 * UMMA_K, bh + k8 * K8_STEP, (kb | k8) != 0);
+              mma(d_tmem, ah + k8 * UMMA_K, bh + LO_STEP + k8 * K8_STEP, 1);
+              mma(d_tmem, ah + (uint32_t)C + k8 * UMMA_K, bh + k8 * K8_STEP, 1);
             }
             release(stage);
             if (kb + 1 == nkb) mma_commit(&T->t_full[as]);
@@ -540,7 +560,11 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       float cmax = 0.f;
 #pragma unroll
       for (int w = 0; w < 2 * NUM_EPI / 32; ++w) cmax = fmaxf(cmax, T->xmax_w[w]);
-      const float margin = 1.1f * 0.0009765625f * sqrtf(xi * cmax) + 1e-30f;
+      // FP16 halves below 2^-14 are subnormal: absolute error 2^-25 per element on top of the
+      // relative one, i.e. at most 2^-24 sqrt(channels) (|x_i| + |x_j|) on the score
+      float margin = 1.1f * 0.0009765625f * sqrtf(xi * cmax) + 1e-30f;
+      if (F16) margin += 5.96e-8f * sqrtf((float)(2 * C)) * (sqrtf(xi) + sqrtf(cmax));
+      if (TERMS == 1) margin = 0.f;   // both sweeps compute the very same scores
       // masked candidates score -inf and must never pass; rows past the end keep nothing
       thr = valid ? fmaxf(tau - margin, -3.0e38f) : CUDART_INF_F;
       asm volatile("bar.sync 3, %0;" ::"n"(2 * NUM_EPI) : "memory");  // bins read: the area may take survivors
@@ -719,6 +743,154 @@ split_tf32_kernel(const float* __restrict__ x, int C, int N, float* __restrict__
   }
 }
 
+// ---- packed-FP16 operands -------------------------------------------------------------------------
+// max |x| over a tensor, kept as the bit pattern of a non-negative float (ordered like an unsigned)
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ amax) {
+  unsigned m = 0u;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n4 = (reinterpret_cast<uintptr_t>(x) & 15u) == 0 ? n / 4 : 0;
+  for (long long q = i; q < n4; q += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + q);
+    m = max(max(m, __float_as_uint(fabsf(v.x))), max(__float_as_uint(fabsf(v.y)),
+            max(__float_as_uint(fabsf(v.z)), __float_as_uint(fabsf(v.w)))));
+  }
+  for (long long q = 4 * n4 + i; q < n; q += stride) m = max(m, __float_as_uint(fabsf(x[q])));
+  m = ecb200::block_max_u32(m);
+  // one of ECB200_AMAX_SLOTS slots per block (no single hot address); monotone, so it is skipped
+  // once the slot is already as large (a stale read only costs a redundant atomic)
+  unsigned* slot = amax + (blockIdx.x & (ECB200_AMAX_SLOTS - 1));
+  if (threadIdx.x == 0 && m > *reinterpret_cast<volatile unsigned*>(slot)) atomicMax(slot, m);
+}
+
+// power of two that moves the tensor's largest magnitude into [2^13, 2^14): hi = fp16(s x) is then a
+// normal number with an 11-bit significand for every element above 2^-27 of the maximum, and
+// lo = fp16(s x - hi) keeps the pair exact to max(2^-22 |s x|, 2^-25)
+__device__ __forceinline__ float f16_scale(unsigned amax_bits) {
+  const float a = __uint_as_float(amax_bits);
+  if (!(a > 0.f) || amax_bits >= 0x7f800000u) return 1.f;   // empty / all-zero / non-finite input
+  int e;
+  (void)frexpf(a, &e);                                      // a = m 2^e, m in [0.5, 1)
+  return ldexpf(1.f, 14 - e);
+}
+
+// x[B,C,N] -> point-major packed halves hh = fp16(s x), hl = fp16(s x - hh) [M,C] and xxs[M] =
+// |s x|^2 (= s^2 |x|^2 exactly: scaling by a power of two commutes with rounding); optionally the
+// tf32 operand pair and |x|^2 of split_tf32_kernel in the same pass over x
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ x, int C, int N, const unsigned* __restrict__ amax,
+                 __half* __restrict__ hh, __half* __restrict__ hl, float* __restrict__ xxs,
+                 float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ xx) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int n0 = blockIdx.x * 32, bb = blockIdx.y;
+  const float* xb = x + (size_t)bb * C * N;
+  __shared__ float s_sh;
+  if (ty == 0) {   // the tensor's max |x| = max over the slots
+    unsigned m = __ldg(amax + tx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (tx == 0) s_sh = f16_scale(m);
+  }
+  __syncthreads();
+  const float s = s_sh;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int c = c0 + ty + 8 * r, n = n0 + tx;
+      tile[ty + 8 * r][tx] = (c < C && n < N) ? xb[(size_t)c * N + n] : 0.f;
+    }
+    __syncthreads();
+    if (hi) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int n = n0 + ty + 8 * r, c = c0 + tx;
+        if (n < N && c < C) {
+          const float v = tile[tx][ty + 8 * r];
+          const float h = to_tf32(v);
+          const size_t o = ((size_t)bb * N + n) * C + c;
+          hi[o] = h;
+          lo[o] = to_tf32(v - h);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {       // 32 points x 16 channel pairs
+      const int p = ty * 32 + tx + 256 * r;
+      const int pn = p >> 4, cp = p & 15;
+      const int n = n0 + pn, c = c0 + 2 * cp;
+      if (n < N && c < C) {             // C is even
+        const float v0 = s * tile[2 * cp][pn], v1 = s * tile[2 * cp + 1][pn];
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        const size_t o = ((size_t)bb * N + n) * C + c;
+        *reinterpret_cast<__half2*>(hh + o) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(hl + o) = __halves2half2(__float2half_rn(v0 - __half2float(h0)),
+                                                             __float2half_rn(v1 - __half2float(h1)));
+      }
+    }
+    __syncthreads();
+  }
+  if (ty == 0 && n0 + tx < N) {  // same summation order as ecb200_sqnorms
+    float a = 0.f, b = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = xb[(size_t)c * N + n0 + tx];
+      a = fmaf(v, v, a);
+      const float w = s * v;
+      b = fmaf(w, w, b);
+    }
+    if (xx) xx[(size_t)bb * N + n0 + tx] = a;
+    xxs[(size_t)bb * N + n0 + tx] = b;
+  }
+}
+
+// xyz layer (C <= 5 channels): all three terms of the compensated product fit ONE 16-deep K step,
+//   query row     A = [ h(0..C-1) | h(0..C-1) | l(0..C-1) | 0 ... ]
+//   candidate row B = [ h(0..C-1) | l(0..C-1) | h(0..C-1) | 0 ... ]      A.B = h.h + h.l + l.h
+// Rows are 128 bytes (one swizzle row); only their first 32 bytes are ever read by the MMAs.
+// One CTA per cloud: it finds the cloud's own largest magnitude first (a cloud is a few KB), so the
+// scale is per cloud and no separate reduction pass is needed.
+template <int C>
+__global__ void __launch_bounds__(1024)
+pack_xyz_f16_kernel(const float* __restrict__ x, int N, __half* __restrict__ arow,
+                    __half* __restrict__ brow, float* __restrict__ xxs) {
+  __shared__ unsigned wmax[32];
+  const int bb = blockIdx.x;
+  const float* xb = x + (size_t)bb * C * N;
+  unsigned m = 0u;
+  for (int i = threadIdx.x; i < C * N; i += blockDim.x) m = max(m, __float_as_uint(fabsf(__ldg(xb + i))));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = wmax[threadIdx.x & 31];
+  if ((threadIdx.x & 31) >= (blockDim.x >> 5)) m = 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float s = f16_scale(m);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    __align__(16) __half a[16], b[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) a[u] = b[u] = __float2half_rn(0.f);
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float v = s * xb[(size_t)c * N + n];
+      q = fmaf(v, v, q);
+      const __half h = __float2half_rn(v);
+      const __half l = __float2half_rn(v - __half2float(h));
+      a[c] = h; a[C + c] = h; a[2 * C + c] = l;
+      b[c] = h; b[C + c] = l; b[2 * C + c] = h;
+    }
+    const size_t o = ((size_t)bb * N + n) * 64;
+    uint4* ad = reinterpret_cast<uint4*>(arow + o);
+    uint4* bd = reinterpret_cast<uint4*>(brow + o);
+    ad[0] = reinterpret_cast<const uint4*>(a)[0]; ad[1] = reinterpret_cast<const uint4*>(a)[1];
+    bd[0] = reinterpret_cast<const uint4*>(b)[0]; bd[1] = reinterpret_cast<const uint4*>(b)[1];
+    xxs[(size_t)bb * N + n] = q;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -770,20 +942,21 @@ int make_operand(OperandMaps* m, const float* hi, const float* lo, long long row
 struct TcArgs {
   const float *a_hi, *a_lo, *b_hi, *b_lo, *xx;
   long long b_rows;   // rows of the B arrays
-  int clouds, C, Na, Nb, k;
+  int clouds, C, Na, Nb, k;   // C in 32-bit words per row (= channels for tf32, channels / 2 for packed fp16)
   int32_t* idx;
   float* dbg;
   long long* tl;
+  int ksteps = KB / UMMA_K;   // K steps per 32-word block that hold data
 };
 
 // clouds = grid.y; per cloud Na rows of A (queries / points) and Nb rows of B (candidates / Wcat rows)
-template <bool DEBUG, int CL, int S, int CAP>
+template <bool DEBUG, int CL, int S, int CAP, bool F16 = false, int TERMS = 3>
 int launch_tc(const TcArgs& a, cudaStream_t st) {
   OperandMaps Bm;
   int rc = make_operand(&Bm, a.b_hi, a.b_lo, a.b_rows, a.C, BM / CL);
   if (rc) return rc;
   const int nkb = a.C / KB;
-  auto kern = knn_tc_kernel<32, DEBUG, CL, S>;
+  auto kern = knn_tc_kernel<32, DEBUG, CL, S, F16, TERMS>;
   constexpr size_t smem = smem_bytes(S, DEBUG ? 0 : CAP);
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static thread_local bool seen[ecb200::kMaxDevices] = {};
@@ -801,7 +974,7 @@ int launch_tc(const TcArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a.a_hi, a.a_lo, Bm.hi, Bm.lo, a.xx, a.Na, a.Nb, nkb, a.k, CAP,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a.a_hi, a.a_lo, Bm.hi, Bm.lo, a.xx, a.Na, a.Nb, nkb, a.ksteps, a.k, CAP,
                                      a.idx, a.dbg, a.tl);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
@@ -841,6 +1014,13 @@ int launch_knn(const TcArgs& a, cudaStream_t st) {
   if (cl == 4) return launch_tc<false, 4, 3, KMAX + GUARD>(a, st);
   if (cl == 2) return launch_tc<false, 2, 3, KMAX + GUARD>(a, st);
   return launch_tc<false, 1, 3, KMAX + GUARD>(a, st);
+}
+
+// packed-FP16 operands (ecb200_split_f16 / ecb200_pack_xyz_f16): no cluster variants
+template <int TERMS>
+int launch_knn_f16(const TcArgs& a, cudaStream_t st) {
+  if (a.k <= 20) return launch_tc<false, 1, 4, 20 + GUARD, true, TERMS>(a, st);
+  return launch_tc<false, 1, 3, KMAX + GUARD, true, TERMS>(a, st);
 }
 
 __global__ void split_rows_tf32_kernel(const float* __restrict__ src, long long n, float* __restrict__ hi,
@@ -885,6 +1065,87 @@ extern "C" int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, 
   ECB_REQUIRE(k <= KMAX, "ecb200_knn_tc: k=%d exceeds %d (use ecb200_knn)", k, KMAX);
   TcArgs a = {hi, lo, hi, lo, xx, (long long)B * N, B, C, N, N, k, idx, nullptr, nullptr};
   return launch_knn(a, (cudaStream_t)stream);
+}
+
+extern "C" int ecb200_absmax(const float* x, long long n, float* amax, void* stream) {
+  ECB_REQUIRE(x && amax && n >= 1, "ecb200_absmax: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  ECB_CUDA(cudaMemsetAsync(amax, 0, ECB200_AMAX_SLOTS * sizeof(float), st));
+  const long long blocks = ecb200::ceil_div64(n, 256 * 16);
+  absmax_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, st>>>(x, n, reinterpret_cast<unsigned*>(amax));
+  ECB_LAUNCH_CHECK("absmax_kernel");
+  return ECB200_OK;
+}
+
+extern "C" int ecb200_split_f16(const float* x, int B, int C, int N, const float* amax, void* hh, void* hl,
+                                float* xxs, float* hi, float* lo, float* xx, void* stream) {
+  ECB_REQUIRE(x && amax && hh && hl && xxs, "ecb200_split_f16: null pointer");
+  ECB_REQUIRE((hi == nullptr) == (lo == nullptr), "ecb200_split_f16: hi and lo come as a pair");
+  ECB_REQUIRE(B >= 1 && B <= 65535 && C >= 2 && C % 2 == 0 && N >= 1, "ecb200_split_f16: bad shape (C must be even)");
+  dim3 grid(ecb200::ceil_div(N, 32), B);
+  split_f16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      x, C, N, reinterpret_cast<const unsigned*>(amax), static_cast<__half*>(hh), static_cast<__half*>(hl), xxs,
+      hi, lo, xx);
+  ECB_LAUNCH_CHECK("split_f16_kernel");
+  return ECB200_OK;
+}
+
+extern "C" int ecb200_pack_xyz_f16(const float* x, int B, int C, int N, void* arow, void* brow, float* xxs,
+                                   void* stream) {
+  ECB_REQUIRE(x && arow && brow && xxs, "ecb200_pack_xyz_f16: null pointer");
+  ECB_REQUIRE(B >= 1 && C >= 1 && C <= 5 && N >= 1, "ecb200_pack_xyz_f16: bad shape (C <= 5)");
+  const int nt = N >= 1024 ? 1024 : 32 * ecb200::ceil_div(N, 32);
+  __half* ar = static_cast<__half*>(arow);
+  __half* br = static_cast<__half*>(brow);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (C) {
+    case 1: pack_xyz_f16_kernel<1><<<B, nt, 0, st>>>(x, N, ar, br, xxs); break;
+    case 2: pack_xyz_f16_kernel<2><<<B, nt, 0, st>>>(x, N, ar, br, xxs); break;
+    case 3: pack_xyz_f16_kernel<3><<<B, nt, 0, st>>>(x, N, ar, br, xxs); break;
+    case 4: pack_xyz_f16_kernel<4><<<B, nt, 0, st>>>(x, N, ar, br, xxs); break;
+    default: pack_xyz_f16_kernel<5><<<B, nt, 0, st>>>(x, N, ar, br, xxs); break;
+  }
+  ECB_LAUNCH_CHECK("pack_xyz_f16_kernel");
+  return ECB200_OK;
+}
+
+extern "C" int ecb200_knn_tc_f16(const void* hh, const void* hl, const float* xxs, int B, int C, int N, int k,
+                                 int32_t* idx, long long* timeline, void* stream) {
+  ECB_REQUIRE(hh && hl && xxs && idx, "ecb200_knn_tc_f16: null pointer");
+  ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1, "ecb200_knn_tc_f16: bad shape B=%d N=%d", B, N);
+  ECB_REQUIRE(C % 64 == 0 && C >= 64 && C <= 2 * KB * MAX_KB,
+              "ecb200_knn_tc_f16: C=%d must be a multiple of 64 in [64, 256]", C);
+  ECB_REQUIRE(k >= 1 && k <= N, "ecb200_knn_tc_f16: k=%d out of range for N=%d (selected index k out of range)", k, N);
+  ECB_REQUIRE(k <= KMAX, "ecb200_knn_tc_f16: k=%d exceeds %d (use ecb200_knn)", k, KMAX);
+  const float* h = static_cast<const float*>(hh);
+  const float* l = static_cast<const float*>(hl);
+  TcArgs a = {h, l, h, l, xxs, (long long)B * N, B, C / 2, N, N, k, idx, nullptr, timeline};
+  return launch_knn_f16<3>(a, (cudaStream_t)stream);
+}
+
+extern "C" int ecb200_knn_tc_xyz(const void* arow, const void* brow, const float* xxs, int B, int N, int k,
+                                 int32_t* idx, long long* timeline, void* stream) {
+  ECB_REQUIRE(arow && brow && xxs && idx, "ecb200_knn_tc_xyz: null pointer");
+  ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1, "ecb200_knn_tc_xyz: bad shape B=%d N=%d", B, N);
+  ECB_REQUIRE(k >= 1 && k <= N, "ecb200_knn_tc_xyz: k=%d out of range for N=%d (selected index k out of range)", k, N);
+  ECB_REQUIRE(k <= KMAX, "ecb200_knn_tc_xyz: k=%d exceeds %d (use ecb200_knn)", k, KMAX);
+  const float* a_ = static_cast<const float*>(arow);
+  const float* b_ = static_cast<const float*>(brow);
+  TcArgs a = {a_, a_, b_, b_, xxs, (long long)B * N, B, KB, N, N, k, idx, nullptr, timeline};
+  a.ksteps = 1;
+  return launch_knn_f16<1>(a, (cudaStream_t)stream);
+}
+
+extern "C" int ecb200_debug_tc_scores_f16(const void* hh, const void* hl, const float* xxs, int B, int C,
+                                          int N, float* scores, void* stream) {
+  ECB_REQUIRE(hh && hl && xxs && scores, "ecb200_debug_tc_scores_f16: null pointer");
+  ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1, "ecb200_debug_tc_scores_f16: bad shape");
+  ECB_REQUIRE(C % 64 == 0 && C >= 64 && C <= 2 * KB * MAX_KB,
+              "ecb200_debug_tc_scores_f16: C=%d must be a multiple of 64 in [64, 256]", C);
+  const float* h = static_cast<const float*>(hh);
+  const float* l = static_cast<const float*>(hl);
+  TcArgs a = {h, l, h, l, xxs, (long long)B * N, B, C / 2, N, N, 1, nullptr, scores, nullptr};
+  return launch_tc<true, 1, 5, 0, true, 3>(a, (cudaStream_t)stream);
 }
 
 extern "C" int ecb200_debug_tc_timeline(const float* hi, const float* lo, const float* xx, int B, int C,

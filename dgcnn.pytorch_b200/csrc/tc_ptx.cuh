@@ -159,6 +159,29 @@ __device__ __forceinline__ void mma_tf32_ts_lo(uint32_t d_tmem, uint32_t a_tmem,
       "r"(a_tmem), "r"(b_desc_lo), "r"(idesc), "r"(accumulate), "n"(SW128_KMAJOR_DESC_HI)
       : "memory");
 }
+// kind::f16 with FP16 operands and FP32 accumulation.  In 32-bit words everything is laid out
+// exactly as for tf32: 16 halves of K = 32 bytes of a shared-memory row = 8 packed columns of
+// tensor memory per instruction, so the tf32 stepping constants carry over unchanged.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4)                 // [4,6)   D format: F32
+         | (0u << 7)               // [7,10)  A format: F16
+         | (0u << 10)              // [10,13) B format: F16
+         | (0u << 15) | (0u << 16) // A, B K-major
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 bd, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_desc_lo), "r"(idesc), "r"(accumulate), "n"(SW128_KMAJOR_DESC_HI)
+      : "memory");
+}
 // 32 registers per thread -> 32 lanes x 32 columns of tensor memory (lane = row)
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(

@@ -98,9 +98,17 @@ def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
     if ops.knn_uses_tensor_cores(C, N, int(k)) or (idx is not None and ops.point_gemm_uses_tensor_cores(C)):
         # feature-space layer: one split into tf32 hi/lo operands feeds both the tensor-core
         # kNN and the tensor-core per-point GEMM
-        xhi, xlo, xx = ops.split_tf32_op(x.detach().contiguous())
-        if idx is None:
-            idx = ops.knn_tc_op(xhi, xlo, xx, B, N, int(k))
+        if idx is None and ops.knn_tc_kind(C, N, int(k)) == "f16":
+            # one pass over x makes the packed fp16 halves of the kNN and the tf32 halves of the GEMMs
+            gemm_tc = ops.point_gemm_uses_tensor_cores(C)
+            hh, hl, xxs, xhi, xlo, _ = ops.split_f16_op(x.detach().contiguous(), gemm_tc, ops.known_amax(x))
+            idx = ops.knn_tc_f16_op(hh, hl, xxs, B, N, int(k))
+            if not gemm_tc:
+                xhi = xlo = None
+        else:
+            xhi, xlo, xx = ops.split_tf32_op(x.detach().contiguous())
+            if idx is None:
+                idx = ops.knn_tc_op(xhi, xlo, xx, B, N, int(k))
     if idx is None:
         # the order over k is irrelevant here, but the xyz graph is asked for again by the callers of
         # knn() / get_graph_feature() on the same tensor (model_partseg.py:26, layers.py:45), which

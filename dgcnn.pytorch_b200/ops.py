@@ -25,6 +25,7 @@ from . import _lib
 
 GF_CONCAT, GF_KNN_ONLY, GF_DISP_ONLY, GF_CONCAT_CENTERED = 0, 1, 2, 3
 MAX_K = 64
+AMAX_SLOTS = 32          # ECB200_AMAX_SLOTS
 
 # torch.distributed process groups cannot travel through an op schema: ops take an
 # integer handle into this table (0 = no cross-rank BatchNorm statistics).
@@ -128,10 +129,16 @@ def knn_op(x: Tensor, k: int, sorted: bool = True) -> Tensor:
     if k > MAX_K:
         raise RuntimeError(f"edgeconv_b200: k={k} exceeds the selector limit {MAX_K}")
     x = x.contiguous()
-    if knn_uses_tensor_cores(C, N, k):
-        # feature-space layers: tcgen05 / TMA distance tiles (knn_tc.cu)
+    kind = knn_tc_kind(C, N, k)
+    if kind == "f16":
+        # feature-space layers: tcgen05 / TMA distance tiles (knn_tc.cu), packed fp16 halves
+        hh, hl, xxs = split_f16_op(x, False)[:3]
+        return knn_tc_f16_op(hh, hl, xxs, B, N, k)
+    if kind == "tf32":
         hi, lo, xx = split_tf32_op(x)
         return knn_tc_op(hi, lo, xx, B, N, k)
+    if kind == "xyz":
+        return knn_tc_xyz_op(x, k)
     with torch.cuda.device(x.device):
         # xyz layer (and any shape the tensor-core kernel does not take): FP32 FMA tiles
         xx = torch.empty(B * N, device=x.device, dtype=torch.float32)
@@ -183,13 +190,133 @@ def _(hi, lo, xx, B, N, k):
     return hi.new_empty((B, N, k), dtype=torch.int32)
 
 
+# ---- packed-FP16 operands (kind::f16): same 11-bit significands as tf32 at twice the MMA rate ----
+@torch.library.custom_op("edgeconv_b200::split_f16", mutates_args=(), device_types="cuda")
+def split_f16_op(x: Tensor, with_tf32: bool, amax: Optional[Tensor] = None) -> List[Tensor]:
+    """x [B,C,N] -> [hh, hl (fp16 [B*N,C]), xxs [B*N], hi, lo (tf32-valued fp32 [B*N,C]), xx [B*N]].
+    hh/hl/xxs are the operands of knn_tc_f16_op (the tensor scaled by a power of two into fp16's
+    range); hi/lo/xx those of the tensor-core GEMMs, from the same pass (empty unless with_tf32).
+    ``amax`` [AMAX_SLOTS]: max |x| when the producer of x already knows it (ecb200_edge_apply_amax)."""
+    _check_cuda_f32("x", x, 3)
+    B, C, N = x.shape
+    x = x.contiguous()
+    dev = x.device
+    with torch.cuda.device(dev):
+        st = _stream(x)
+        hh = torch.empty(B * N, C, device=dev, dtype=torch.float16)
+        hl = torch.empty(B * N, C, device=dev, dtype=torch.float16)
+        xxs = torch.empty(B * N, device=dev, dtype=torch.float32)
+        hi = lo = xx = None
+        if with_tf32:
+            hi = torch.empty(B * N, C, device=dev, dtype=torch.float32)
+            lo = torch.empty(B * N, C, device=dev, dtype=torch.float32)
+            xx = torch.empty(B * N, device=dev, dtype=torch.float32)
+        if amax is None:
+            amax = torch.empty(AMAX_SLOTS, device=dev, dtype=torch.float32)
+            _lib.call("ecb200_absmax", _ptr(x), x.numel(), _ptr(amax), st)
+        _lib.call("ecb200_split_f16", _ptr(x), B, C, N, _ptr(amax), _ptr(hh), _ptr(hl), _ptr(xxs),
+                  _ptr(hi), _ptr(lo), _ptr(xx), st)
+    if not with_tf32:
+        hi, lo, xx = xxs.new_empty(0), xxs.new_empty(0), xxs.new_empty(0)
+    return [hh, hl, xxs, hi, lo, xx]
+
+
+@split_f16_op.register_fake
+def _(x, with_tf32, amax=None):
+    B, C, N = x.shape
+    h = x.new_empty((B * N, C), dtype=torch.float16)
+    f = x.new_empty((B * N, C)) if with_tf32 else x.new_empty(0)
+    v = x.new_empty((B * N,)) if with_tf32 else x.new_empty(0)
+    return [h, x.new_empty((B * N, C), dtype=torch.float16), x.new_empty((B * N,)), f,
+            x.new_empty((B * N, C)) if with_tf32 else x.new_empty(0), v]
+
+
+@torch.library.custom_op("edgeconv_b200::knn_tc_f16", mutates_args=(), device_types="cuda")
+def knn_tc_f16_op(hh: Tensor, hl: Tensor, xxs: Tensor, B: int, N: int, k: int) -> Tensor:
+    """kNN graph from the packed fp16 operands: int32 [B,N,k], nearest first."""
+    C = hh.shape[1]
+    if k > N or k < 1:
+        raise RuntimeError(f"selected index k out of range (k={k}, N={N})")
+    with torch.cuda.device(hh.device):
+        idx = torch.empty(B, N, k, device=hh.device, dtype=torch.int32)
+        _lib.call("ecb200_knn_tc_f16", _ptr(hh), _ptr(hl), _ptr(xxs), B, C, N, k, _ptr(idx), None, _stream(hh))
+    return idx
+
+
+@knn_tc_f16_op.register_fake
+def _(hh, hl, xxs, B, N, k):
+    return hh.new_empty((B, N, k), dtype=torch.int32)
+
+
+@torch.library.custom_op("edgeconv_b200::knn_tc_xyz", mutates_args=(), device_types="cuda")
+def knn_tc_xyz_op(x: Tensor, k: int) -> Tensor:
+    """kNN of a low-dimensional cloud (C <= 5, the xyz layer) on the tensor-core pipeline: the
+    three terms of the compensated product of a point sit in ONE 16-deep K step."""
+    _check_cuda_f32("x", x, 3)
+    B, C, N = x.shape
+    if k > N or k < 1:
+        raise RuntimeError(f"selected index k out of range (k={k}, N={N})")
+    x = x.contiguous()
+    dev = x.device
+    with torch.cuda.device(dev):
+        st = _stream(x)
+        rows = torch.empty(2, B * N, 64, device=dev, dtype=torch.float16)
+        xxs = torch.empty(B * N, device=dev, dtype=torch.float32)
+        idx = torch.empty(B, N, k, device=dev, dtype=torch.int32)
+        _lib.call("ecb200_pack_xyz_f16", _ptr(x), B, C, N, _ptr(rows[0]), _ptr(rows[1]), _ptr(xxs), st)
+        _lib.call("ecb200_knn_tc_xyz", _ptr(rows[0]), _ptr(rows[1]), _ptr(xxs), B, N, k, _ptr(idx), None, st)
+    return idx
+
+
+@knn_tc_xyz_op.register_fake
+def _(x, k):
+    B, C, N = x.shape
+    return x.new_empty((B, N, k), dtype=torch.int32)
+
+
+def knn_tc_kind(C: int, N: int, k: int) -> str:
+    """Which tensor-core kernel knn() uses: "f16" (packed fp16 halves, C a multiple of 64), "tf32"
+    (C a multiple of 32), "xyz" (C <= 5, N >= 64) or "" (FP32-FMA kernel).  ECB200_KNN=fma|tf32 and
+    ECB200_KNN_XYZ=fma override (A/B tests)."""
+    mode = os.environ.get("ECB200_KNN", "auto")
+    if mode == "fma" or k > 40:
+        return ""
+    if C <= 5:
+        return "xyz" if (N >= 64 and os.environ.get("ECB200_KNN_XYZ", "tc") == "tc") else ""
+    if C % 64 == 0 and 64 <= C <= 256 and mode != "tf32":
+        return "f16"
+    if C % 32 == 0 and 32 <= C <= 128:
+        return "tf32"
+    return ""
+
+
 def knn_uses_tensor_cores(C: int, N: int, k: int) -> bool:
     """Kernel choice for knn(): tensor cores where the contraction is a real GEMM
     (C a multiple of 32 in [32, 128], k <= 40), FP32 FMA otherwise (any C, k <= 64).
     ECB200_KNN=fma forces the FMA kernel (A/B tests)."""
-    if os.environ.get("ECB200_KNN", "auto") == "fma":
-        return False
-    return C % 32 == 0 and 32 <= C <= 128 and k <= 40
+    return knn_tc_kind(C, N, k) in ("f16", "tf32")
+
+
+def debug_tc_scores_f16(x: Tensor) -> Tensor:
+    """Diagnostic: scores x_i.x_j - 0.5|x_j|^2 [B,N,N] from the packed-fp16 pipeline (unscaled)."""
+    _check_cuda_f32("x", x, 3)
+    B, C, N = x.shape
+    x = x.contiguous()
+    with torch.cuda.device(x.device):
+        amax = torch.empty(AMAX_SLOTS, device=x.device, dtype=torch.float32)
+        hh = torch.empty(B * N, C, device=x.device, dtype=torch.float16)
+        hl = torch.empty_like(hh)
+        xxs = torch.empty(B * N, device=x.device, dtype=torch.float32)
+        out = torch.full((B, N, N), float("nan"), device=x.device, dtype=torch.float32)
+        st = _stream(x)
+        _lib.call("ecb200_absmax", _ptr(x), x.numel(), _ptr(amax), st)
+        _lib.call("ecb200_split_f16", _ptr(x), B, C, N, _ptr(amax), _ptr(hh), _ptr(hl), _ptr(xxs), None, None,
+                  None, st)
+        _lib.call("ecb200_debug_tc_scores_f16", _ptr(hh), _ptr(hl), _ptr(xxs), B, C, N, _ptr(out), st)
+        import math
+        e = math.frexp(float(amax.max()))[1] if float(amax.max()) > 0 else 14
+        s = 2.0 ** (14 - e)
+    return out / (s * s)
 
 
 def debug_tc_scores(x: Tensor) -> Tensor:
@@ -282,9 +409,10 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
                     use_batch_stats: bool, eps: float, slope: float, subtract_center: bool,
                     group: int, save_for_bwd: bool, xhi: Optional[Tensor],
                     xlo: Optional[Tensor], emit_pm: bool) -> List[Tensor]:
-    """Returns [out, out_pm, sel, arg, esum, Y, Wcat, affine, stats, wsplit]; ``out_pm`` [B*N, Co] is the
-    same output point-major (rows of channels; empty unless ``emit_pm``); ``affine`` is [4,Co] =
-    (mean, invstd, a, b).  Everything after ``out_pm`` exists for the backward pass."""
+    """Returns [out, out_pm, sel, arg, esum, Y, Wcat, affine, stats, wsplit, amax]; ``out_pm`` [B*N, Co] is
+    the same output point-major (rows of channels; empty unless ``emit_pm``); ``affine`` is [4,Co] =
+    (mean, invstd, a, b); ``amax`` [AMAX_SLOTS] = max |out| (the next layer's operand scale).  Everything
+    between ``out_pm`` and ``amax`` exists for the backward pass."""
     _check_cuda_f32("x", x, 3)
     B, C, N = x.shape
     k = idx.shape[-1]
@@ -335,15 +463,16 @@ def edgeconv_fwd_op(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta:
         else:
             _lib.call("ecb200_bn_finalize", None, _ptr(gamma_c), _ptr(beta_c), _ptr(running_mean),
                       _ptr(running_var), 0, float(eps), Co, mean, invstd, a, b, st)
-        _lib.call("ecb200_edge_apply", _ptr(sel), a, b, float(slope), B, N, Co, _ptr(out), _ptr(out_pm),
-                  Co, st)
+        amax = torch.empty(AMAX_SLOTS, **f32)
+        _lib.call("ecb200_edge_apply_amax", _ptr(sel), a, b, float(slope), B, N, Co, _ptr(out), _ptr(out_pm),
+                  Co, _ptr(amax), st)
     if esum is None:
         esum = sel.new_empty(0)
     if out_pm is None:
         out_pm = sel.new_empty(0)
     if wsplit is None:
         wsplit = sel.new_empty(0)
-    return [out, out_pm, sel, arg, esum, Y, Wcat, affine, stats, wsplit]
+    return [out, out_pm, sel, arg, esum, Y, Wcat, affine, stats, wsplit, amax]
 
 
 @edgeconv_fwd_op.register_fake
@@ -357,7 +486,7 @@ def _(x, idx, weight, gamma, beta, running_mean, running_var, use_batch_stats, e
             f((M, Co)) if save_for_bwd else f((0,)), f((M, 2 * Co)), f((2 * Co, C)),
             f((4, Co)), f((2 * Co + 1,), dtype=torch.float64),
             f((4, 2 * Co * C)) if (xhi is not None and xlo is not None and point_gemm_uses_tensor_cores(C))
-            else f((0,))]
+            else f((0,)), f((AMAX_SLOTS,))]
 
 
 @torch.library.custom_op("edgeconv_b200::edgeconv_bwd", mutates_args=(), device_types="cuda")
@@ -452,7 +581,7 @@ def _(gout, gout_pm, x, idx, sel, arg, esum, wsplit, Y, Wcat, affine, stats, use
 def _ec_setup(ctx, inputs, output):
     (x, idx, weight, gamma, beta, _rm, _rv, use_batch_stats, _eps, slope, subtract_center, group,
      save_for_bwd, _xhi, _xlo, _emit_pm) = inputs
-    out, out_pm, sel, arg, esum, Y, Wcat, affine, stats, wsplit = output
+    out, out_pm, sel, arg, esum, Y, Wcat, affine, stats, wsplit = output[:10]
     if not save_for_bwd:
         raise RuntimeError("edgeconv_b200: forward ran with save_for_bwd=False but a gradient "
                            "is required")
@@ -522,9 +651,19 @@ def edgeconv(x: Tensor, idx: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor
                           xhi, xlo, bool(return_point_major))
     if update_running:
         bn_update_running_op(res[8].detach(), running_mean, running_var, num_batches_tracked, mom)
+    # side channel to the next layer's ecb200_split_f16: valid while `out` is not written in place
+    res[0]._ecb200_amax = (res[10].detach(), res[0]._version)
     if return_point_major:
         return res[0], res[1]          # [B,Co,N] and the same values as [B*N, Co]
     return res[0]
+
+
+def known_amax(x: Tensor) -> Optional[Tensor]:
+    """max |x| [1] if x is the untouched output of edgeconv() (which measured it while writing x)."""
+    tag = getattr(x, "_ecb200_amax", None)
+    if tag is not None and tag[1] == x._version and tag[0].device == x.device:
+        return tag[0]
+    return None
 
 
 # ------------------------------------------- conv5's BN + LeakyReLU + global max|avg pooling
@@ -848,7 +987,8 @@ def knn_cached(x: Tensor, k: int, sorted: bool = True) -> Tensor:
 # computes in fp32 (3xTF32 on the tensor cores): every op casts its floating-point inputs to fp32
 # and runs with autocast disabled.  Gradients are linear in the incoming gradient, so GradScaler's
 # loss scaling and its inf/nan detection pass through unchanged.
-for _op in (knn_op, split_tf32_op, knn_tc_op, graph_feature_op, graph_feature_bwd_op, edgeconv_fwd_op,
+# (knn_tc_f16_op is left out on purpose: its operands ARE fp16 bit patterns made by split_f16_op)
+for _op in (knn_op, split_tf32_op, knn_tc_op, split_f16_op, knn_tc_xyz_op, graph_feature_op, graph_feature_bwd_op, edgeconv_fwd_op,
             edgeconv_bwd_op, embed_pool_fwd_op, embed_pool_bwd_op, embed_gemm_op):
     _op.register_autocast("cuda", torch.float32)
 

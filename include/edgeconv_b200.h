@@ -45,6 +45,7 @@ extern "C" {
 
 #define ECB200_VERSION 100            /* major*100 + minor */
 #define ECB200_MAX_K 64               /* neighbours per point supported by the selector */
+#define ECB200_AMAX_SLOTS 32          /* floats of an `amax` buffer (ecb200_absmax, ecb200_edge_apply_amax) */
 
 enum {
   ECB200_OK = 0,
@@ -94,6 +95,33 @@ int ecb200_knn_tc(const float* hi, const float* lo, const float* xx, int B, int 
                   void* stream);
 int ecb200_debug_tc_scores(const float* hi, const float* lo, const float* xx, int B, int C, int N,
                            float* scores, void* stream);
+/* The same kNN with packed FP16 operands (tcgen05 kind::f16): fp16 and tf32 carry the same 11-bit
+ * significand, so the compensated product hi.hi + hi.lo + lo.hi is as accurate as 3xTF32 once the
+ * tensor has been moved into fp16's range by a power of two -- at twice the tensor-pipe rate.
+ *   ecb200_absmax:       max_s amax[s] = max |x| over n values; amax has ECB200_AMAX_SLOTS floats
+ *                        (several slots, so that thousands of blocks do not hammer one address; the
+ *                        callee zero-fills them first, consumers take the maximum over the slots)
+ *   ecb200_split_f16:    s = 2^(14 - exponent(amax)); hh = fp16(s x), hl = fp16(s x - hh), point-major
+ *                        [B*N, C] halves (C even), xxs[B*N] = s^2 |x|^2; optionally (hi/lo/xx non-NULL)
+ *                        the outputs of ecb200_split_tf32 from the same pass over x
+ *   ecb200_knn_tc_f16:   idx as ecb200_knn (nearest first); C a multiple of 64 in [64,256], k <= 40;
+ *                        `timeline` NULL, or the diagnostic buffer of ecb200_debug_tc_timeline
+ *   ecb200_pack_xyz_f16 / ecb200_knn_tc_xyz: the xyz layer (C <= 5) on the same pipeline -- the three
+ *                        terms of a point's compensated product sit side by side in ONE 16-deep K
+ *                        step (query rows [h|h|l], candidate rows [h|l|h], 128-byte rows), one MMA
+ *                        per 128 x 128 tile and sweep; the scale is per cloud, found by the pack kernel
+ *   ecb200_debug_tc_scores_f16: diagnostic -- s^2 (x_i.x_j - 0.5|x_j|^2) [B,N,N] */
+int ecb200_absmax(const float* x, long long n, float* amax, void* stream);
+int ecb200_split_f16(const float* x, int B, int C, int N, const float* amax, void* hh, void* hl,
+                     float* xxs, float* hi, float* lo, float* xx, void* stream);
+int ecb200_knn_tc_f16(const void* hh, const void* hl, const float* xxs, int B, int C, int N, int k,
+                      int32_t* idx, long long* timeline, void* stream);
+int ecb200_pack_xyz_f16(const float* x, int B, int C, int N, void* arow, void* brow, float* xxs,
+                        void* stream);
+int ecb200_knn_tc_xyz(const void* arow, const void* brow, const float* xxs, int B, int N, int k,
+                      int32_t* idx, long long* timeline, void* stream);
+int ecb200_debug_tc_scores_f16(const void* hh, const void* hl, const float* xxs, int B, int C,
+                               int N, float* scores, void* stream);
 /* hi = tf32(src), lo = tf32(src - hi), element-wise over n values (operand prep for the
  * tensor-core GEMM: Wcat is already K-major) */
 int ecb200_split_rows_tf32(const float* src, long long n, float* hi, float* lo, void* stream);
@@ -169,6 +197,11 @@ int ecb200_bn_update_running(const double* stats, int Co, float momentum, float*
  * 512-channel concat in front of conv5, dgcnn.py:100).  Either of out / out_pm may be NULL. */
 int ecb200_edge_apply(const float* sel, const float* a, const float* b, float slope, int B,
                       int N, int Co, float* out, float* out_pm, long long ld_pm, void* stream);
+/* The same, and max_s amax[s] = max |out| (ECB200_AMAX_SLOTS floats, zero-filled by the callee first): the next layer's operand
+ * scale for ecb200_split_f16, so the activations need no separate reduction pass. */
+int ecb200_edge_apply_amax(const float* sel, const float* a, const float* b, float slope, int B,
+                           int N, int Co, float* out, float* out_pm, long long ld_pm, float* amax,
+                           void* stream);
 
 /* ---- EdgeConv backward ------------------------------------------------------------ */
 

@@ -16,13 +16,13 @@ if len(sys.argv) > 1 and sys.argv[1].startswith("model"):
     torch.manual_seed(1)
     net = ec.DGCNN_cls(SimpleNamespace(emb_dims=1024, k=k, dropout=0.5)).to(dev).train()
     seen = []
-    orig = ec.ops.split_tf32_op
-    def spy(x):
+    orig = ec.ops.split_f16_op
+    def spy(x, *rest):
         seen.append(x.detach().clone())
-        return orig(x)
-    ec.ops.split_tf32_op = spy
+        return orig(x, *rest)
+    ec.ops.split_f16_op = spy
     import dgcnn_pytorch_b200.dgcnn as dg
-    dg.ops.split_tf32_op = spy
+    dg.ops.split_f16_op = spy
     with torch.no_grad():
         net(orc.synthetic_xyz(B, N, seed=100).to(dev))
     x = seen[layer - 2].contiguous()
@@ -30,23 +30,35 @@ if len(sys.argv) > 1 and sys.argv[1].startswith("model"):
     print(f"layer {layer} input: C={C}, mean {x.mean():.3f} std {x.std():.3f}")
 else:
     B, C, N, k = (int(v) for v in (sys.argv[1].split(",") if len(sys.argv) > 1 else "32,64,1024,20".split(",")))
-    x = orc.synthetic_features(B, C, N, seed=1).to(dev)
+    x = (orc.synthetic_xyz(B, N, seed=1) if C == 3 else orc.synthetic_features(B, C, N, seed=1)).to(dev)
+KIND = os.environ.get("TL_KIND", "xyz" if C <= 5 else "f16")   # f16 | tf32 | xyz
 hi = torch.empty(B * N, C, device=dev); lo = torch.empty_like(hi); xx = torch.empty(B * N, device=dev)
 idx = torch.empty(B, N, k, device=dev, dtype=torch.int32)
 nb = L.load().ecb200_knn_tc_workspace_bytes(B, N, k)
 ws = torch.empty(nb, device=dev, dtype=torch.uint8)
 ntile = B * ((N + 127) // 128)
 tl = torch.zeros(6 * 256 + 3 * ntile, device=dev, dtype=torch.int64)
-P = lambda t: c_void_p(t.data_ptr())
+P = lambda t: None if t is None else c_void_p(t.data_ptr())
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
 L.call("ecb200_split_tf32", P(x), B, C, N, P(hi), P(lo), P(xx), st)
+if KIND == "f16":
+    hh, hl, xxs = ec.ops.split_f16_op(x, False)[:3]
+    launch = lambda t: L.call("ecb200_knn_tc_f16", P(hh), P(hl), P(xxs), B, C, N, k, P(idx), t, st)
+elif KIND == "xyz":
+    rows = torch.empty(2, B * N, 64, device=dev, dtype=torch.float16); xxs = torch.empty(B * N, device=dev)
+    L.call("ecb200_pack_xyz_f16", P(x), B, C, N, P(rows[0]), P(rows[1]), P(xxs), st)
+    launch = lambda t: L.call("ecb200_knn_tc_xyz", P(rows[0]), P(rows[1]), P(xxs), B, N, k, P(idx), t, st)
+else:
+    launch = lambda t: (L.call("ecb200_debug_tc_timeline", P(hi), P(lo), P(xx), B, C, N, k, P(idx), P(ws), t, st) if t is not None
+                        else L.call("ecb200_knn_tc", P(hi), P(lo), P(xx), B, C, N, k, 1, P(idx), P(ws), nb, st))
+print("kernel kind:", KIND)
 for _ in range(3):
-    L.call("ecb200_debug_tc_timeline", P(hi), P(lo), P(xx), B, C, N, k, P(idx), P(ws), P(tl), st)
+    launch(P(tl))
 torch.cuda.synchronize()
 allc = tl.cpu()[6 * 256:].view(ntile, 3)
 t = tl.cpu()[:6 * 256].view(6, 256)
 t0 = int(t[5, 0])
-nct = (N + 127) // 128; nkb = C // 32
+nct = (N + 127) // 128; nkb = max(1, C // (64 if KIND != "tf32" else 32))
 rel = lambda v: (int(v) - t0) if int(v) else None
 print("producer stage-acquire times (first 20, last 4):", [rel(v) for v in t[0, :20]], [rel(v) for v in t[0, 2 * nct * nkb - 4:2 * nct * nkb]])
 print("mma per tile (start, commit):")
@@ -79,17 +91,17 @@ print(f"  first wave: {int(first.sum())} CTAs, duration median {dur[first].media
 # warm, back-to-back launches timed with CUDA events (sustained clocks), and the SM clock implied by
 # CTA (0,0): cycles between its first and last stamp vs its wall-clock duration
 for _ in range(5):
-    L.call("ecb200_knn_tc", P(hi), P(lo), P(xx), B, C, N, k, 1, P(idx), P(ws), nb, st)
+    launch(None)
 torch.cuda.synchronize()
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
 for _ in range(50):
-    L.call("ecb200_knn_tc", P(hi), P(lo), P(xx), B, C, N, k, 1, P(idx), P(ws), nb, st)
+    launch(None)
 e.record()
 torch.cuda.synchronize()
 us = s.elapsed_time(e) * 1e3 / 50
 print(f"50 back-to-back launches: {us:.1f} us each = {2.0 * B * N * N * C / us / 1e6:.1f} TFLOP/s "
-      f"({2.0 * B * N * N * C / us / 1e6 / 268.2:.3f} of the 3xTF32 roofline 268.2)")
+      f"({2.0 * B * N * N * C / us / 1e6 / 268.2:.3f} of the 3xTF32 roofline 268.2, {2.0 * B * N * N * C / us / 1e6 / 536.4:.3f} of the 3xFP16 roofline 536.4)")
 import numpy as np
 d = dur.numpy(); bg = beg.numpy(); sm = allc[:, 2].numpy()
 nrt = (N + 127) // 128
