@@ -310,7 +310,7 @@ def gather_kernel_bytes(M, k, Co, training=True):
 
 
 # forward kernels of the EdgeConv path (kNN + edge MLP + max), by name fragments of the kernels
-EDGE_FWD_KERNELS = ("knn_tc_kernel<32, false", "knn_tc_kernel<32, 0", "knn_xyz_kernel", "knn_fma_kernel", "sqnorms_kernel",
+EDGE_FWD_KERNELS = ("knn_tc_kernel<32, false", "knn_tc_kernel<32, 0", "knn_tc2_kernel", "knn_xyz_kernel", "knn_fma_kernel", "sqnorms_kernel",
                     "split_tf32_kernel", "split_f16_kernel", "pack_xyz_f16_kernel", "absmax_kernel",
                     "prepare_weights_kernel", "pack_weight_kernel", "gemm_tile_kernel", "knn_tc_kernel<32, true", "edge_gather_kernel",
                     "bn_finalize_kernel", "edge_apply_kernel", "bn_update_running_kernel")
@@ -565,14 +565,18 @@ def run_b200(a):
             return None, None
         t, f16 = 0.0, False
         for n, v in kprof.items():
-            if not (n.startswith("knn_tc_kernel<32, false") or n.startswith("knn_tc_kernel<32, 0")):
+            if n.startswith("knn_tc2_kernel<"):          # 256-row variant: packed fp16 only, <TERMS>
+                is_xyz, is_f16 = n.rstrip(">").split("<")[-1].strip() == "1", True
+            elif n.startswith("knn_tc_kernel<32, false") or n.startswith("knn_tc_kernel<32, 0"):
+                tail = n.rstrip(">").split(",")[-2:]
+                is_xyz = len(n.split(",")) >= 6 and tail[-1].strip() == "1"
+                is_f16 = len(n.split(",")) >= 6 and tail[0].strip() in ("true", "1")
+            else:
                 continue
-            tail = n.rstrip(">").split(",")[-2:]
-            is_xyz = len(n.split(",")) >= 6 and tail[-1].strip() == "1"
             if is_xyz != xyz:
                 continue
             t += v["us_per_step"]
-            f16 = f16 or (len(n.split(",")) >= 6 and tail[0].strip() in ("true", "1"))
+            f16 = f16 or is_f16
         return (t or None), f16
     t_us, knn_f16 = knn_tc_us(False)
     src = "in-graph (CUPTI)"
@@ -620,7 +624,7 @@ def run_b200(a):
     xyz_kernel = "knn_xyz_kernel"
     t_us = kernel_us("knn_xyz_kernel")
     if not t_us and knn_tc_us(True)[0]:
-        t_us, xyz_kernel = knn_tc_us(True)[0], "knn_tc_kernel<.., F16, TERMS = 1> (one kind::f16 MMA per 128x128 tile and sweep)"
+        t_us, xyz_kernel = knn_tc_us(True)[0], "tensor-core kNN, TERMS = 1 (one kind::f16 MMA per tile and sweep; knn_tc2_kernel<1> or knn_tc_kernel<.., true, 1>)"
     if not t_us and entry_ms("ecb200_knn_tc_xyz"):
         t_us, xyz_kernel = entry_ms("ecb200_knn_tc_xyz") * 1e3, "ecb200_knn_tc_xyz (eager brackets)"
     if not t_us and entry_ms("ecb200_knn"):

@@ -24,15 +24,16 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "topk_select.cuh"
+#include "knn_tc_shared.cuh"
 
 namespace {
 
 using namespace ecb200::tc;
 using namespace ecb200::topk;
+using namespace ecb200::knntc;
 
 constexpr int BM = 128;                  // query rows per CTA (= TMEM lanes)
 constexpr int BN = 128;                  // candidates per MMA tile (= TMEM columns per stage)
-constexpr int KB = 32;                   // channels per K-block: 32 fp32 = one 128-byte swizzle row
 constexpr int TILE_BYTES = BM * KB * 4;  // 16 KB: one K-block of one operand half
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // a ring stage: (hi | lo) of a K-block, or two hi K-blocks
 constexpr int MAX_KB = 4;                // C <= 128 keeps the query tile resident
@@ -58,53 +59,6 @@ struct SharedTail {  // lives after the operand ring and the survivor lists
 __host__ __device__ constexpr size_t smem_bytes(int S, int cap) {
   return 1024 /* alignment slack */ + (size_t)S * STAGE_BYTES + (size_t)cap * LS * sizeof(uint64_t) +
          sizeof(SharedTail);
-}
-
-template <int NBINS>
-__device__ __forceinline__ void sort_bins_desc(float (&v)[NBINS]) {
-#pragma unroll
-  for (int size = 2; size <= NBINS; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-#pragma unroll
-      for (int i = 0; i < NBINS; ++i) {
-        const int j = i ^ stride;
-        if (j > i) {
-          const bool desc = (i & size) == 0;
-          const float a = v[i], b = v[j];
-          v[i] = desc ? fmaxf(a, b) : fminf(a, b);
-          v[j] = desc ? fminf(a, b) : fmaxf(a, b);
-        }
-      }
-    }
-  }
-}
-
-// raw survivor entry (score bits << 32 | j) -> totally ordered key (larger score, then smaller j)
-__device__ __forceinline__ uint64_t ordered_key(uint64_t raw) {
-  return make_key(__uint_as_float((uint32_t)(raw >> 32)), (int)(uint32_t)raw);
-}
-// Overflow of a thread's survivor list (only with massive ties or clustered data): keep its own
-// best k entries in place and return the score a later candidate must reach to matter ("strictly
-// better than the k-th kept": later candidates of equal score have a larger j, hence a smaller
-// key).  Out of line and not unrolled: it must not bloat the hot loop's instruction footprint.
-__device__ __noinline__ float shrink_survivors(uint64_t* buf, int cnt, int k) {
-#pragma unroll 1
-  while (cnt > k) {
-    int arg = 0;
-    uint64_t mn = ordered_key(buf[0]);
-#pragma unroll 1
-    for (int e = 1; e < cnt; ++e) {
-      const uint64_t w = ordered_key(buf[e * LS]);
-      if (w < mn) { mn = w; arg = e; }
-    }
-    --cnt;
-    buf[arg * LS] = buf[cnt * LS];
-  }
-  uint64_t mn = ordered_key(buf[0]);
-#pragma unroll 1
-  for (int e = 1; e < cnt; ++e) mn = min(mn, ordered_key(buf[e * LS]));
-  return nextafterf(key_score(mn), CUDART_INF_F);
 }
 
 // Optional timeline (diagnostics): CTA (0,0) stamps clock64() into tl[role*256 + i]
@@ -454,7 +408,7 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
 #pragma unroll
             for (int h = 0; h < 32 / GUARD; ++h) {
               if (cnt > cap - GUARD) {  // rare (ties, clustered data): keep the thread's own best k
-                thr = fmaxf(thr, shrink_survivors(sv, cnt, k));
+                thr = fmaxf(thr, shrink_survivors(sv, cnt, k, LS));
                 cnt = k;
               }
 #pragma unroll
@@ -577,7 +531,7 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
         // most k entries of a list can make the row's top k).  Never taken with the 4-stage ring.
         constexpr int UNI_HALF = S * STAGE_BYTES / 1024 / 2;
         if (cnt > UNI_HALF) {
-          shrink_survivors(sv, cnt, k);
+          shrink_survivors(sv, cnt, k, LS);
           cnt = k;
         }
       }
@@ -891,54 +845,6 @@ pack_xyz_f16_kernel(const float* __restrict__ x, int N, __half* __restrict__ aro
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// [rows, C] fp32 row-major, box = 32 channels x box_rows rows, 128-byte swizzle, zero fill past the end
-int make_point_map(CUtensorMap* m, const float* p, long long rows, int C, int box_rows) {
-  EncodeTiledFn enc = encode_fn();
-  if (!enc) {
-    ecb200::set_error("cuTensorMapEncodeTiled is not available from this driver");
-    return ECB200_ERR_CUDA;
-  }
-  const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)C * sizeof(float)};
-  const cuuint32_t box[2] = {KB, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    ecb200::set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return ECB200_ERR_CUDA;
-  }
-  return ECB200_OK;
-}
-
-// [rows, C] fp32 row-major operand pair (hi, lo) as TMA maps
-struct OperandMaps {
-  CUtensorMap hi, lo;
-};
-int make_operand(OperandMaps* m, const float* hi, const float* lo, long long rows, int C, int box_rows) {
-  int rc = make_point_map(&m->hi, hi, rows, C, box_rows);
-  if (rc) return rc;
-  return make_point_map(&m->lo, lo, rows, C, box_rows);
-}
-
 struct TcArgs {
   const float *a_hi, *a_lo, *b_hi, *b_lo, *xx;
   long long b_rows;   // rows of the B arrays
@@ -1119,6 +1025,10 @@ extern "C" int ecb200_knn_tc_f16(const void* hh, const void* hl, const float* xx
   ECB_REQUIRE(k <= KMAX, "ecb200_knn_tc_f16: k=%d exceeds %d (use ecb200_knn)", k, KMAX);
   const float* h = static_cast<const float*>(hh);
   const float* l = static_cast<const float*>(hl);
+  if (tc2_takes(C / 2, N, k, 3)) {   // 256 query rows per CTA, four epilogue warpgroups (knn_tc2.cu)
+    Tc2Args a2 = {h, l, h, l, xxs, (long long)B * N, B, C / 2, N, k, KB / UMMA_K, idx, timeline};
+    return launch_knn_tc2(a2, 3, (cudaStream_t)stream);
+  }
   TcArgs a = {h, l, h, l, xxs, (long long)B * N, B, C / 2, N, N, k, idx, nullptr, timeline};
   return launch_knn_f16<3>(a, (cudaStream_t)stream);
 }
@@ -1131,6 +1041,10 @@ extern "C" int ecb200_knn_tc_xyz(const void* arow, const void* brow, const float
   ECB_REQUIRE(k <= KMAX, "ecb200_knn_tc_xyz: k=%d exceeds %d (use ecb200_knn)", k, KMAX);
   const float* a_ = static_cast<const float*>(arow);
   const float* b_ = static_cast<const float*>(brow);
+  if (tc2_takes(KB, N, k, 1)) {
+    Tc2Args a2 = {a_, a_, b_, b_, xxs, (long long)B * N, B, KB, N, k, 1, idx, timeline};
+    return launch_knn_tc2(a2, 1, (cudaStream_t)stream);
+  }
   TcArgs a = {a_, a_, b_, b_, xxs, (long long)B * N, B, KB, N, N, k, idx, nullptr, timeline};
   a.ksteps = 1;
   return launch_knn_f16<1>(a, (cudaStream_t)stream);

@@ -117,6 +117,58 @@ def test_knn_vs_oracle(ec, B, C, N, k, kind):
     assert rep["differing_rows"] <= max(2, rep["rows"] // 200), rep
 
 
+@pytest.mark.parametrize("env,B,C,N,k,kind", [
+    # every kernel variant on the shapes it serves, forced through its switch
+    ({"ECB200_KNN": "tf32"}, 2, 64, 1024, 20, "feat"),           # tf32 halves (kind::tf32), also C = 32 / 96 by default
+    ({"ECB200_KNN": "tf32"}, 1, 128, 640, 40, "feat"),
+    ({"ECB200_KNN_ROWS": "128"}, 2, 64, 1024, 20, "feat"),       # packed fp16 halves, 128 query rows per CTA
+    ({"ECB200_KNN_ROWS": "256"}, 2, 64, 1024, 20, "feat"),       # ... 256 query rows per CTA (knn_tc2.cu)
+    ({"ECB200_KNN_ROWS": "256"}, 3, 128, 700, 17, "feat"),       # ragged: partial second row tile, odd tile count
+    ({"ECB200_KNN_ROWS": "256"}, 2, 64, 130, 20, "feat"),        # second row tile nearly empty
+    ({"ECB200_KNN_ROWS": "128"}, 4, 3, 1024, 20, "xyz"),         # xyz on the tensor cores, both row counts
+    ({"ECB200_KNN_ROWS": "256"}, 4, 3, 1024, 20, "xyz"),
+    ({"ECB200_KNN_ROWS": "256"}, 2, 3, 2500, 9, "xyz"),
+    ({"ECB200_KNN_XYZ": "fma"}, 4, 3, 1024, 20, "xyz"),          # FP32-FMA kernel (the round-1 path)
+    ({"ECB200_KNN": "fma"}, 2, 64, 512, 20, "feat"),
+])
+def test_knn_kernel_variants_vs_oracle(ec, monkeypatch, env, B, C, N, k, kind):
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    x = orc.synthetic_xyz(B, N, seed=B + N) if kind == "xyz" else orc.synthetic_features(B, C, N, seed=C + N)
+    rep = check_knn(ec, x, k)
+    assert rep["differing_rows"] <= max(2, rep["rows"] // 200), rep
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-4, 3e4, 1e-18, 1e15])
+def test_knn_fp16_operands_are_scale_free(ec, scale):
+    """The packed-fp16 operands are moved into fp16's range by a power of two measured from the
+    tensor itself: the graph must not depend on the magnitude of the features."""
+    x = orc.synthetic_features(2, 64, 512, seed=11)
+    ref = ec.knn(x.to(dev()), 20).cpu()
+    got = ec.knn((x * scale).to(dev()), 20).cpu()
+    rep = orc.knn_mismatch_report(x, got, ref, rel_eps=TIE_EPS)
+    assert rep["bad_rows"] == 0, rep
+    xyz = orc.synthetic_xyz(2, 700, seed=3)
+    rep = orc.knn_mismatch_report(xyz, ec.knn((xyz * scale).to(dev()), 16).cpu(), orc.knn_oracle(xyz, 16), rel_eps=TIE_EPS)
+    assert rep["bad_rows"] == 0, rep
+
+
+def test_knn_fp16_score_accuracy_and_degenerate_inputs(ec):
+    x = orc.synthetic_features(2, 128, 256, seed=5).to(dev())
+    xd = x.double()
+    ref = torch.einsum("bci,bcj->bij", xd, xd) - 0.5 * (xd * xd).sum(1)[:, None, :]
+    err = (ec.ops.debug_tc_scores_f16(x).double() - ref).abs().max().item() / (xd * xd).sum(1).max().item()
+    assert err < 4e-6, err            # same bound as the 3xTF32 products (1.8e-6 measured there)
+    # all-zero input: every point is every point's neighbour at distance 0 -> smallest indices first
+    z = torch.zeros(1, 64, 300, device=dev())
+    idx = ec.knn(z, 5)
+    assert torch.equal(idx[0, 17].cpu(), torch.arange(5))
+    # huge dynamic range inside one tensor: a far-away cluster must not disturb the near one
+    y = orc.synthetic_xyz(1, 600, seed=9)
+    y[:, :, 300:] = y[:, :, 300:] * 1e-3 + 50.0
+    check_knn(ec, y, 12)
+
+
 def test_knn_self_is_first_and_deterministic(ec):
     x = orc.synthetic_xyz(4, 512, seed=9).to(dev())
     a, b = ec.knn(x, 20), ec.knn(x, 20)
