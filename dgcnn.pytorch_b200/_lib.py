@@ -23,11 +23,11 @@ SIGNATURES = {
     "ecb200_knn_tc": (P, P, P, I, I, I, I, I, P, P, Z, P),
     "ecb200_debug_tc_scores": (P, P, P, I, I, I, P, P),
     "ecb200_absmax": (P, LL, P, P),
-    "ecb200_split_f16": (P, I, I, I, P, P, P, P, P, P, P, P),
-    "ecb200_knn_tc_f16": (P, P, P, I, I, I, I, P, P, P),
-    "ecb200_pack_xyz_f16": (P, I, I, I, P, P, P, P),
-    "ecb200_knn_tc_xyz": (P, P, P, I, I, I, P, P, P),
-    "ecb200_debug_tc_scores_f16": (P, P, P, I, I, I, P, P),
+    "ecb200_split_f16": (P, I, I, I, P, P, P, P, P, P, P, P, P, P),
+    "ecb200_knn_tc_f16": (P, P, P, P, P, I, I, I, I, P, P, P),
+    "ecb200_pack_xyz_f16": (P, I, I, I, P, P, P, P, P),
+    "ecb200_knn_tc_xyz": (P, P, P, P, I, I, I, P, P, P),
+    "ecb200_debug_tc_scores_f16": (P, P, I, I, I, P, P),
     "ecb200_debug_tc_timeline": (P, P, P, I, I, I, I, P, P, P, P),
     "ecb200_split_rows_tf32": (P, LL, P, P, P),
     "ecb200_point_gemm_tc": (P, P, P, P, LL, I, I, P, P),

@@ -53,6 +53,7 @@ struct SharedTail {  // lives after the operand ring and the survivor lists
   float xmax_w[2 * NUM_EPI / 32];  // per-warp max |x_j|^2 over the candidates it staged
   uint64_t a_full, b_full[8], b_empty[8], t_full[2], t_empty[2];
   uint32_t tmem_slot;
+  float cmax_s;                    // FOLD: the cloud's max |s x_j|^2
 };
 
 // shared memory: [S ring stages of 32 KB][cap survivor slots x 256 threads x 8 bytes][tail]
@@ -82,11 +83,18 @@ __host__ __device__ constexpr size_t smem_bytes(int S, int cap) {
 //               3-channel point sit side by side in ONE 16-deep K step), both passes issue the same
 //               single MMA and no margin is needed.
 // ksteps:       K steps per 32-word block that hold data (4; 1 for the packed xyz operands).
-template <int NBINS, bool DEBUG, int CL, int S, bool F16 = false, int TERMS = 3>
+// FOLD:         (packed FP16 only) the column term -0.5*|x_j|^2 is part of the contraction: three more K
+//               slots hold 2^15 on the query side and the three FP16 pieces of -|s x_j|^2 / 2^16 on the
+//               candidate side (the operands are scaled into [2^11, 2^12) so that the term fits FP16's
+//               range), so the epilogue neither adds nor stages anything per candidate.  With TERMS = 3
+//               the slots are one extra K step whose candidate rows come from `map_bn`; with TERMS = 1
+//               they sit in free slots of the one K step.  cmax_g[b] = max_j |s x_j|^2 of cloud b.
+template <int NBINS, bool DEBUG, int CL, int S, bool F16 = false, int TERMS = 3, bool FOLD = false>
 __global__ void __launch_bounds__(NT, 1)
 knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g,
               const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-              const float* __restrict__ xx, int Na, int N, int nkb, int ksteps, int k, int cap,
+              const __grid_constant__ CUtensorMap map_bn, const float* __restrict__ xx,
+              const float* __restrict__ cmax_g, int Na, int N, int nkb, int ksteps, int k, int cap,
               int32_t* __restrict__ idx, float* __restrict__ dbg, long long* tl) {
   // A operand: rows [b*Na + rt*128, +128) of a_hi_g / a_lo_g [*, C] (the queries; for the GEMM use
   // the points), copied ONCE into tensor memory (lane = row, column = channel): the MMAs then
@@ -161,7 +169,25 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
         if (CL > 1) tma_load_2d_mc(dst + slice_off, m, bar, c0, r0 + (int)crank * SLICE_ROWS, CMASK);
         else        tma_load_2d(dst, m, bar, c0, r0);
       };
-      if (!DEBUG) {
+      if (!DEBUG && FOLD && TERMS == 3) {
+        // first sweep: nkb hi K-blocks + the norm block of every tile, two blocks per stage
+        for (int ct = 0; ct < nct; ++ct)
+          for (int u0 = 0; u0 <= nkb; u0 += 2, ++n) {
+            const int nun = min(2, nkb + 1 - u0);
+            mbar_wait(&T->b_empty[stage], phase ^ 1);
+            if (elect_one_sync()) {
+              ECB_STAMP(0, n);
+              unsigned char* dst = b_st + (size_t)stage * STAGE_BYTES;
+              mbar_expect_tx(&T->b_full[stage], nun * TILE_BYTES);
+              for (int j = 0; j < nun; ++j) {
+                if (u0 + j < nkb) load(dst + j * TILE_BYTES, &map_bhi, &T->b_full[stage], (u0 + j) * KB, cloud_row0 + ct * BN);
+                else              load(dst + j * TILE_BYTES, &map_bn, &T->b_full[stage], 0, cloud_row0 + ct * BN);
+              }
+            }
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+      } else if (!DEBUG) {
         for (int sweep = 0; sweep < (TERMS == 1 ? 2 : 1); ++sweep)
         for (int ct = 0; ct < nct; ++ct)
           for (int kb = 0; kb < nkb; kb += kpa, ++n) {
@@ -179,14 +205,19 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       }
       if (TERMS == 3)
       for (int ct = 0; ct < nct; ++ct)
-        for (int kb = 0; kb < nkb; ++kb, ++n) {
+        for (int kb = 0; kb < nkb + ((FOLD && !DEBUG) ? 1 : 0); ++kb, ++n) {
           mbar_wait(&T->b_empty[stage], phase ^ 1);
           if (elect_one_sync()) {
             ECB_STAMP(0, n);
             unsigned char* dst = b_st + (size_t)stage * STAGE_BYTES;
-            mbar_expect_tx(&T->b_full[stage], 2 * TILE_BYTES);
-            load(dst, &map_bhi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
-            load(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+            if (kb < nkb) {
+              mbar_expect_tx(&T->b_full[stage], 2 * TILE_BYTES);
+              load(dst, &map_bhi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+              load(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+            } else {   // the norm block of the tile, a stage of its own
+              mbar_expect_tx(&T->b_full[stage], TILE_BYTES);
+              load(dst, &map_bn, &T->b_full[stage], 0, cloud_row0 + ct * BN);
+            }
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -213,7 +244,40 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
         if (CL > 1) mma_commit_mc(&T->b_empty[st], CMASK);
         else        mma_commit(&T->b_empty[st]);
       };
-      if (!DEBUG) {
+      const uint32_t a_norm = a_col + (uint32_t)(2 * C);   // FOLD: the 2^15 constants behind the hi | lo halves
+      if (!DEBUG && FOLD && TERMS == 3) {
+        // first sweep with the norm block: units 0..nkb-1 = hi K-blocks, unit nkb = norm, two per stage
+        for (int ct = 0; ct < nct; ++ct, ++tile) {
+          const int as = tile & 1;
+          mbar_wait(&T->t_empty[as], ((tile >> 1) & 1) ^ 1);
+          tc_fence_after();
+          ECB_STAMP(1, 2 * tile);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+          for (int u0 = 0; u0 <= nkb; u0 += 2) {
+            const int nun = min(2, nkb + 1 - u0);
+            mbar_wait(&T->b_full[stage], phase);
+            tc_fence_after();
+            const uint32_t bh = ring_lo + (uint32_t)stage * STAGE_STEP;
+            if (elect_one_sync()) {
+              for (int j = 0; j < nun; ++j) {
+                if (u0 + j < nkb) {
+                  const uint32_t ah = a_col + (uint32_t)((u0 + j) * KB);
+#pragma unroll
+                  for (int k8 = 0; k8 < KB / UMMA_K; ++k8)
+                    mma(d_tmem, ah + k8 * UMMA_K, bh + j * LO_STEP + k8 * K8_STEP, (u0 | j | k8) != 0);
+                } else {
+                  mma(d_tmem, a_norm, bh + j * LO_STEP, 1);
+                }
+              }
+              release(stage);
+              if (u0 + 2 > nkb) mma_commit(&T->t_full[as]);
+            }
+            __syncwarp();
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+          ECB_STAMP(1, 2 * tile + 1);
+        }
+      } else if (!DEBUG) {
         // pass A: one product of the hi halves (ranked with an error margin), two K-blocks per stage;
         // with TERMS == 1 the second sweep is the same again
         for (int sweep = 0; sweep < (TERMS == 1 ? 2 : 1); ++sweep)
@@ -252,20 +316,25 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
         tc_fence_after();
         ECB_STAMP(1, 2 * tile);
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int nst = nkb + ((FOLD && !DEBUG) ? 1 : 0);   // + the norm block's stage
+        for (int kb = 0; kb < nst; ++kb) {
           mbar_wait(&T->b_full[stage], phase);
           tc_fence_after();
           const uint32_t ah = a_col + (uint32_t)(kb * KB);  // tensor-memory columns of A hi; lo at +C
           const uint32_t bh = ring_lo + (uint32_t)stage * STAGE_STEP;
           if (elect_one_sync()) {
+            if (kb < nkb) {
 #pragma unroll
-            for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
-              mma(d_tmem, ah + k8 * UMMA_K, bh + k8 * K8_STEP, (kb | k8) != 0);
-              mma(d_tmem, ah + k8 * UMMA_K, bh + LO_STEP + k8 * K8_STEP, 1);
-              mma(d_tmem, ah + (uint32_t)C + k8 * UMMA_K, bh + k8 * K8_STEP, 1);
+              for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
+                mma(d_tmem, ah + k8 * UMMA_K, bh + k8 * K8_STEP, (kb | k8) != 0);
+                mma(d_tmem, ah + k8 * UMMA_K, bh + LO_STEP + k8 * K8_STEP, 1);
+                mma(d_tmem, ah + (uint32_t)C + k8 * UMMA_K, bh + k8 * K8_STEP, 1);
+              }
+            } else {
+              mma(d_tmem, a_norm, bh, 1);
             }
             release(stage);
-            if (kb + 1 == nkb) mma_commit(&T->t_full[as]);
+            if (kb + 1 == nst) mma_commit(&T->t_full[as]);
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -314,9 +383,25 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
         __syncwarp();
         tmem_st_32x32(dst + (uint32_t)c0, r);
       }
+      if (FOLD && TERMS == 3 && !DEBUG && g == 0) {
+        // the query side of the norm block: 2^15 (0x7800) in its first three K slots, the same for every row
+        uint32_t r[8] = {0x78007800u, 0x00007800u, 0u, 0u, 0u, 0u, 0u, 0u};
+        __syncwarp();
+        tmem_st_32x8(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + (uint32_t)(2 * C), r);
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&T->a_full);
+    }
+    if (FOLD && !DEBUG && warp == 2) {
+      // the cloud's largest squared norm from the per-block maxima of the operand kernel (read by every
+      // epilogue thread after the bar.sync of the threshold stage)
+      const int nblk = (N + 31) / 32;
+      float m = 0.f;
+      for (int i = lane; i < nblk; i += 32) m = fmaxf(m, __ldg(cmax_g + (size_t)b * nblk + i));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) T->cmax_s = m;
     }
     float bin[NBINS];
 #pragma unroll
@@ -339,7 +424,7 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       return (xx && j < N) ? __ldg(xx + cloud_row0 + j) : (xx ? -1.f : 0.f);
     };
     int xnext_t = g & 1;
-    float xnext = load_xx(xnext_t);
+    float xnext = (FOLD && !DEBUG) ? 0.f : load_xx(xnext_t);
     // the tile loop of one pass; `pass` is a compile-time constant in each instantiation, so the
     // two passes get separate code (and register allocations: the bins die after the first)
     auto run_tiles = [&](auto pass_tag) {
@@ -348,7 +433,7 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       for (int ct = (tile0 + g) & 1; ct < nct; ct += 2, ++use) {
         float* hx = T->hx[g][use & 1];
         if (et == 0) ECB_STAMP(2 + g, 4 * use);
-        {
+        if (!FOLD || DEBUG) {
           // |x_j|^2 of this tile's column was fetched one tile ahead (an L2 round trip off the
           // critical path); now fetch the next tile's (or the first tile's of the next pass)
           if (xnext_t != ct) xnext = load_xx(ct);  // only when a pass has no tile for this group
@@ -360,8 +445,10 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
           xmax = fmaxf(xmax, xj);
           hx[et] = xx ? ((xj >= 0.f) ? -0.5f * xj : -CUDART_INF_F) : 0.f;
         }
-        if (g == 0) asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI) : "memory");
-        else        asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI) : "memory");
+        if (!FOLD || DEBUG) {
+          if (g == 0) asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI) : "memory");
+          else        asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPI) : "memory");
+        }
         if (et == 0) ECB_STAMP(2 + g, 4 * use + 1);
         mbar_wait(&T->t_full[g], use & 1);
         tc_fence_after();
@@ -370,13 +457,25 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
         auto process = [&](const uint32_t(&cur)[32], const int c4, const bool second_pass) {
           const float4* hx4 = reinterpret_cast<const float4*>(hx + c4 * 32);
           float v[32];
+          if (FOLD && !DEBUG) {
+            // the accumulator already is the score; only the ragged last tile needs its columns past the
+            // end of the cloud masked (warp-uniform branch)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 h4 = hx4[e];
-            v[4 * e + 0] = __uint_as_float(cur[4 * e + 0]) + h4.x;
-            v[4 * e + 1] = __uint_as_float(cur[4 * e + 1]) + h4.y;
-            v[4 * e + 2] = __uint_as_float(cur[4 * e + 2]) + h4.z;
-            v[4 * e + 3] = __uint_as_float(cur[4 * e + 3]) + h4.w;
+            for (int u = 0; u < 32; ++u) v[u] = __uint_as_float(cur[u]);
+            if ((ct + 1) * BN > N) {
+#pragma unroll
+              for (int u = 0; u < 32; ++u)
+                if (ct * BN + c4 * 32 + u >= N) v[u] = -CUDART_INF_F;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 h4 = hx4[e];
+              v[4 * e + 0] = __uint_as_float(cur[4 * e + 0]) + h4.x;
+              v[4 * e + 1] = __uint_as_float(cur[4 * e + 1]) + h4.y;
+              v[4 * e + 2] = __uint_as_float(cur[4 * e + 2]) + h4.z;
+              v[4 * e + 3] = __uint_as_float(cur[4 * e + 3]) + h4.w;
+            }
           }
           if (DEBUG) {  // dense store of the tile: raw scores, or the GEMM result Y = A.B^T
             if (valid) {
@@ -512,8 +611,12 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       // |x_i||hi_j|) <= 1.1 * 2^-10 |x_i| max_j|x_j|.  Lowering the bound by that margin keeps
       // it a lower bound of the row's k-th best 3xTF32 score (a few more survivors, no misses).
       float cmax = 0.f;
+      if (FOLD) {
+        cmax = T->cmax_s;
+      } else {
 #pragma unroll
-      for (int w = 0; w < 2 * NUM_EPI / 32; ++w) cmax = fmaxf(cmax, T->xmax_w[w]);
+        for (int w = 0; w < 2 * NUM_EPI / 32; ++w) cmax = fmaxf(cmax, T->xmax_w[w]);
+      }
       // FP16 halves below 2^-14 are subnormal: absolute error 2^-25 per element on top of the
       // relative one, i.e. at most 2^-24 sqrt(channels) (|x_i| + |x_j|) on the score
       float margin = 1.1f * 0.0009765625f * sqrtf(xi * cmax) + 1e-30f;
@@ -718,15 +821,25 @@ absmax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ a
   if (threadIdx.x == 0 && m > *reinterpret_cast<volatile unsigned*>(slot)) atomicMax(slot, m);
 }
 
-// power of two that moves the tensor's largest magnitude into [2^13, 2^14): hi = fp16(s x) is then a
-// normal number with an 11-bit significand for every element above 2^-27 of the maximum, and
-// lo = fp16(s x - hi) keeps the pair exact to max(2^-22 |s x|, 2^-25)
+// power of two that moves the tensor's largest magnitude into [2^11, 2^12): hi = fp16(s x) is then a
+// normal number with an 11-bit significand for every element above 2^-25 of the maximum,
+// lo = fp16(s x - hi) keeps the pair exact to max(2^-22 |s x|, 2^-25), and |s x_j|^2 / 2^16 <= 2^15
+// for up to 128 channels, i.e. the column term -0.5 |x_j|^2 fits three FP16 pieces (norm_pieces)
 __device__ __forceinline__ float f16_scale(unsigned amax_bits) {
   const float a = __uint_as_float(amax_bits);
   if (!(a > 0.f) || amax_bits >= 0x7f800000u) return 1.f;   // empty / all-zero / non-finite input
   int e;
   (void)frexpf(a, &e);                                      // a = m 2^e, m in [0.5, 1)
-  return ldexpf(1.f, 14 - e);
+  return ldexpf(1.f, 12 - e);
+}
+// -0.5 q = 2^15 * (p0 + p1 + p2) with FP16 pieces p (q = |s x_j|^2 <= 2^31): exact to 2^-33 relative
+__device__ __forceinline__ void norm_pieces(float q, __half (&p)[3]) {
+  float w = -q * (1.f / 65536.f);
+  p[0] = __float2half_rn(w);
+  w -= __half2float(p[0]);
+  p[1] = __float2half_rn(w);
+  w -= __half2float(p[1]);
+  p[2] = __float2half_rn(w);
 }
 
 // x[B,C,N] -> point-major packed halves hh = fp16(s x), hl = fp16(s x - hh) [M,C] and xxs[M] =
@@ -734,7 +847,8 @@ __device__ __forceinline__ float f16_scale(unsigned amax_bits) {
 // tf32 operand pair and |x|^2 of split_tf32_kernel in the same pass over x
 __global__ void __launch_bounds__(256)
 split_f16_kernel(const float* __restrict__ x, int C, int N, const unsigned* __restrict__ amax,
-                 __half* __restrict__ hh, __half* __restrict__ hl, float* __restrict__ xxs,
+                 __half* __restrict__ hh, __half* __restrict__ hl, __half* __restrict__ nb,
+                 float* __restrict__ xxs, float* __restrict__ cmax,
                  float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ xx) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -795,38 +909,54 @@ split_f16_kernel(const float* __restrict__ x, int C, int N, const unsigned* __re
     }
     if (xx) xx[(size_t)bb * N + n0 + tx] = a;
     xxs[(size_t)bb * N + n0 + tx] = b;
+    // the norm block's candidate row: [p0 p1 p2 0 ... 0] in the first 32 bytes of a 128-byte row
+    __align__(16) __half r[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) r[u] = __float2half_rn(0.f);
+    __half pc[3];
+    norm_pieces(b, pc);
+    r[0] = pc[0]; r[1] = pc[1]; r[2] = pc[2];
+    uint4* nd = reinterpret_cast<uint4*>(nb + ((size_t)bb * N + n0 + tx) * 64);
+    nd[0] = reinterpret_cast<const uint4*>(r)[0];
+    nd[1] = reinterpret_cast<const uint4*>(r)[1];
+  }
+  if (ty == 0) {   // the cloud's max |s x_j|^2 (margin of the first sweep)
+    float b = (n0 + tx < N) ? xxs[(size_t)bb * N + n0 + tx] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if (tx == 0) cmax[(size_t)bb * gridDim.x + blockIdx.x] = b;   // per-block maxima: no atomics, no zero-fill
   }
 }
 
-// xyz layer (C <= 5 channels): all three terms of the compensated product fit ONE 16-deep K step,
-//   query row     A = [ h(0..C-1) | h(0..C-1) | l(0..C-1) | 0 ... ]
-//   candidate row B = [ h(0..C-1) | l(0..C-1) | h(0..C-1) | 0 ... ]      A.B = h.h + h.l + l.h
+// xyz layer (C <= 4 channels): all three terms of the compensated product AND the column term fit ONE
+// 16-deep K step,
+//   query row     A = [ h(0..C-1) | h(0..C-1) | l(0..C-1) | 2^15 2^15 2^15 | 0 ... ]
+//   candidate row B = [ h(0..C-1) | l(0..C-1) | h(0..C-1) |  p0   p1   p2  | 0 ... ]
+//   A.B = h.h + h.l + l.h - 0.5 |s x_j|^2
 // Rows are 128 bytes (one swizzle row); only their first 32 bytes are ever read by the MMAs.
-// One CTA per cloud: it finds the cloud's own largest magnitude first (a cloud is a few KB), so the
-// scale is per cloud and no separate reduction pass is needed.
+// Every CTA (256 points of one cloud) first finds the cloud's own largest magnitude -- a cloud is a few KB,
+// re-read by each of its CTAs from L2 -- so the scale is per cloud and no separate reduction pass is needed.
 template <int C>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 pack_xyz_f16_kernel(const float* __restrict__ x, int N, __half* __restrict__ arow,
-                    __half* __restrict__ brow, float* __restrict__ xxs) {
-  __shared__ unsigned wmax[32];
-  const int bb = blockIdx.x;
+                    __half* __restrict__ brow, float* __restrict__ xxs, float* __restrict__ cmax) {
+  static_assert(3 * C + 3 <= 16, "three product terms and the norm term must fit one 16-deep K step");
+  __shared__ unsigned m_s;
+  const int bb = blockIdx.y;
   const float* xb = x + (size_t)bb * C * N;
   unsigned m = 0u;
+#pragma unroll 8
   for (int i = threadIdx.x; i < C * N; i += blockDim.x) m = max(m, __float_as_uint(fabsf(__ldg(xb + i))));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  m = ecb200::block_max_u32(m);
+  if (threadIdx.x == 0) m_s = m;
   __syncthreads();
-  m = wmax[threadIdx.x & 31];
-  if ((threadIdx.x & 31) >= (blockDim.x >> 5)) m = 0u;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-  const float s = f16_scale(m);
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+  const float s = f16_scale(m_s);
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  float q = 0.f;
+  if (n < N) {
     __align__(16) __half a[16], b[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) a[u] = b[u] = __float2half_rn(0.f);
-    float q = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float v = s * xb[(size_t)c * N + n];
@@ -836,6 +966,14 @@ pack_xyz_f16_kernel(const float* __restrict__ x, int N, __half* __restrict__ aro
       a[c] = h; a[C + c] = h; a[2 * C + c] = l;
       b[c] = h; b[C + c] = l; b[2 * C + c] = h;
     }
+    // the column term -0.5 |s x_j|^2 in three more slots: 2^15 on the query side, its pieces on the other
+    __half pc[3];
+    norm_pieces(q, pc);
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      a[3 * C + u] = __ushort_as_half((unsigned short)0x7800);
+      b[3 * C + u] = pc[u];
+    }
     const size_t o = ((size_t)bb * N + n) * 64;
     uint4* ad = reinterpret_cast<uint4*>(arow + o);
     uint4* bd = reinterpret_cast<uint4*>(brow + o);
@@ -843,6 +981,10 @@ pack_xyz_f16_kernel(const float* __restrict__ x, int N, __half* __restrict__ aro
     bd[0] = reinterpret_cast<const uint4*>(b)[0]; bd[1] = reinterpret_cast<const uint4*>(b)[1];
     xxs[(size_t)bb * N + n] = q;
   }
+  // per-32-point maxima of |s x_j|^2, the layout ecb200_split_f16 writes
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q = fmaxf(q, __shfl_xor_sync(0xffffffffu, q, o));
+  if ((threadIdx.x & 31) == 0 && n < N) cmax[(size_t)bb * ((N + 31) / 32) + (n >> 5)] = q;
 }
 
 struct TcArgs {
@@ -853,16 +995,23 @@ struct TcArgs {
   float* dbg;
   long long* tl;
   int ksteps = KB / UMMA_K;   // K steps per 32-word block that hold data
+  const float* bn = nullptr;  // FOLD: norm rows [b_rows, 32 words] (TERMS = 3)
+  const float* cmax = nullptr;  // FOLD: per-cloud max |s x_j|^2
 };
 
 // clouds = grid.y; per cloud Na rows of A (queries / points) and Nb rows of B (candidates / Wcat rows)
-template <bool DEBUG, int CL, int S, int CAP, bool F16 = false, int TERMS = 3>
+template <bool DEBUG, int CL, int S, int CAP, bool F16 = false, int TERMS = 3, bool FOLD = false>
 int launch_tc(const TcArgs& a, cudaStream_t st) {
   OperandMaps Bm;
   int rc = make_operand(&Bm, a.b_hi, a.b_lo, a.b_rows, a.C, BM / CL);
   if (rc) return rc;
+  CUtensorMap Bn = Bm.hi;   // placeholder unless the norm block is a separate operand
+  if (FOLD && TERMS == 3) {
+    rc = make_point_map(&Bn, a.bn, a.b_rows, KB, BM / CL);
+    if (rc) return rc;
+  }
   const int nkb = a.C / KB;
-  auto kern = knn_tc_kernel<32, DEBUG, CL, S, F16, TERMS>;
+  auto kern = knn_tc_kernel<32, DEBUG, CL, S, F16, TERMS, FOLD>;
   constexpr size_t smem = smem_bytes(S, DEBUG ? 0 : CAP);
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static thread_local bool seen[ecb200::kMaxDevices] = {};
@@ -880,8 +1029,8 @@ int launch_tc(const TcArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a.a_hi, a.a_lo, Bm.hi, Bm.lo, a.xx, a.Na, a.Nb, nkb, a.ksteps, a.k, CAP,
-                                     a.idx, a.dbg, a.tl);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a.a_hi, a.a_lo, Bm.hi, Bm.lo, Bn, a.xx, a.cmax, a.Na, a.Nb, nkb,
+                                     a.ksteps, a.k, CAP, a.idx, a.dbg, a.tl);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     ecb200::set_error("launch of knn_tc_kernel failed: %s", cudaGetErrorString(e));
@@ -925,8 +1074,8 @@ int launch_knn(const TcArgs& a, cudaStream_t st) {
 // packed-FP16 operands (ecb200_split_f16 / ecb200_pack_xyz_f16): no cluster variants
 template <int TERMS>
 int launch_knn_f16(const TcArgs& a, cudaStream_t st) {
-  if (a.k <= 20) return launch_tc<false, 1, 4, 20 + GUARD, true, TERMS>(a, st);
-  return launch_tc<false, 1, 3, KMAX + GUARD, true, TERMS>(a, st);
+  if (a.k <= 20) return launch_tc<false, 1, 4, 20 + GUARD, true, TERMS, true>(a, st);
+  return launch_tc<false, 1, 3, KMAX + GUARD, true, TERMS, true>(a, st);
 }
 
 __global__ void split_rows_tf32_kernel(const float* __restrict__ src, long long n, float* __restrict__ hi,
@@ -984,81 +1133,87 @@ extern "C" int ecb200_absmax(const float* x, long long n, float* amax, void* str
 }
 
 extern "C" int ecb200_split_f16(const float* x, int B, int C, int N, const float* amax, void* hh, void* hl,
-                                float* xxs, float* hi, float* lo, float* xx, void* stream) {
-  ECB_REQUIRE(x && amax && hh && hl && xxs, "ecb200_split_f16: null pointer");
+                                void* nb, float* xxs, float* cmax, float* hi, float* lo, float* xx,
+                                void* stream) {
+  ECB_REQUIRE(x && amax && hh && hl && nb && xxs && cmax, "ecb200_split_f16: null pointer");
   ECB_REQUIRE((hi == nullptr) == (lo == nullptr), "ecb200_split_f16: hi and lo come as a pair");
-  ECB_REQUIRE(B >= 1 && B <= 65535 && C >= 2 && C % 2 == 0 && N >= 1, "ecb200_split_f16: bad shape (C must be even)");
+  ECB_REQUIRE(B >= 1 && B <= 65535 && C >= 2 && C % 2 == 0 && C <= 128 && N >= 1,
+              "ecb200_split_f16: bad shape (C must be even and at most 128)");
   dim3 grid(ecb200::ceil_div(N, 32), B);
   split_f16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
-      x, C, N, reinterpret_cast<const unsigned*>(amax), static_cast<__half*>(hh), static_cast<__half*>(hl), xxs,
-      hi, lo, xx);
+      x, C, N, reinterpret_cast<const unsigned*>(amax), static_cast<__half*>(hh), static_cast<__half*>(hl),
+      static_cast<__half*>(nb), xxs, cmax, hi, lo, xx);
   ECB_LAUNCH_CHECK("split_f16_kernel");
   return ECB200_OK;
 }
 
 extern "C" int ecb200_pack_xyz_f16(const float* x, int B, int C, int N, void* arow, void* brow, float* xxs,
-                                   void* stream) {
-  ECB_REQUIRE(x && arow && brow && xxs, "ecb200_pack_xyz_f16: null pointer");
-  ECB_REQUIRE(B >= 1 && C >= 1 && C <= 5 && N >= 1, "ecb200_pack_xyz_f16: bad shape (C <= 5)");
-  const int nt = N >= 1024 ? 1024 : 32 * ecb200::ceil_div(N, 32);
+                                   float* cmax, void* stream) {
+  ECB_REQUIRE(x && arow && brow && xxs && cmax, "ecb200_pack_xyz_f16: null pointer");
+  ECB_REQUIRE(B >= 1 && B <= 65535 && C >= 1 && C <= 4 && N >= 1, "ecb200_pack_xyz_f16: bad shape (C <= 4)");
   __half* ar = static_cast<__half*>(arow);
   __half* br = static_cast<__half*>(brow);
   cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(ecb200::ceil_div(N, 256), B);
   switch (C) {
-    case 1: pack_xyz_f16_kernel<1><<<B, nt, 0, st>>>(x, N, ar, br, xxs); break;
-    case 2: pack_xyz_f16_kernel<2><<<B, nt, 0, st>>>(x, N, ar, br, xxs); break;
-    case 3: pack_xyz_f16_kernel<3><<<B, nt, 0, st>>>(x, N, ar, br, xxs); break;
-    case 4: pack_xyz_f16_kernel<4><<<B, nt, 0, st>>>(x, N, ar, br, xxs); break;
-    default: pack_xyz_f16_kernel<5><<<B, nt, 0, st>>>(x, N, ar, br, xxs); break;
+    case 1: pack_xyz_f16_kernel<1><<<grid, 256, 0, st>>>(x, N, ar, br, xxs, cmax); break;
+    case 2: pack_xyz_f16_kernel<2><<<grid, 256, 0, st>>>(x, N, ar, br, xxs, cmax); break;
+    case 3: pack_xyz_f16_kernel<3><<<grid, 256, 0, st>>>(x, N, ar, br, xxs, cmax); break;
+    default: pack_xyz_f16_kernel<4><<<grid, 256, 0, st>>>(x, N, ar, br, xxs, cmax); break;
   }
   ECB_LAUNCH_CHECK("pack_xyz_f16_kernel");
   return ECB200_OK;
 }
 
-extern "C" int ecb200_knn_tc_f16(const void* hh, const void* hl, const float* xxs, int B, int C, int N, int k,
-                                 int32_t* idx, long long* timeline, void* stream) {
-  ECB_REQUIRE(hh && hl && xxs && idx, "ecb200_knn_tc_f16: null pointer");
+extern "C" int ecb200_knn_tc_f16(const void* hh, const void* hl, const void* nb, const float* xxs,
+                                 const float* cmax, int B, int C, int N, int k, int32_t* idx, long long* timeline,
+                                 void* stream) {
+  ECB_REQUIRE(hh && hl && nb && xxs && cmax && idx, "ecb200_knn_tc_f16: null pointer");
   ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1, "ecb200_knn_tc_f16: bad shape B=%d N=%d", B, N);
-  ECB_REQUIRE(C % 64 == 0 && C >= 64 && C <= 2 * KB * MAX_KB,
-              "ecb200_knn_tc_f16: C=%d must be a multiple of 64 in [64, 256]", C);
+  ECB_REQUIRE(C == 64 || C == 128, "ecb200_knn_tc_f16: C=%d must be 64 or 128", C);
   ECB_REQUIRE(k >= 1 && k <= N, "ecb200_knn_tc_f16: k=%d out of range for N=%d (selected index k out of range)", k, N);
   ECB_REQUIRE(k <= KMAX, "ecb200_knn_tc_f16: k=%d exceeds %d (use ecb200_knn)", k, KMAX);
   const float* h = static_cast<const float*>(hh);
   const float* l = static_cast<const float*>(hl);
   if (tc2_takes(C / 2, N, k, 3)) {   // 256 query rows per CTA, four epilogue warpgroups (knn_tc2.cu)
-    Tc2Args a2 = {h, l, h, l, xxs, (long long)B * N, B, C / 2, N, k, KB / UMMA_K, idx, timeline};
+    Tc2Args a2 = {h, l, h, l, static_cast<const float*>(nb), xxs, cmax, (long long)B * N, B, C / 2, N, k,
+                  KB / UMMA_K, idx, timeline};
     return launch_knn_tc2(a2, 3, (cudaStream_t)stream);
   }
   TcArgs a = {h, l, h, l, xxs, (long long)B * N, B, C / 2, N, N, k, idx, nullptr, timeline};
+  a.bn = static_cast<const float*>(nb);
+  a.cmax = cmax;
   return launch_knn_f16<3>(a, (cudaStream_t)stream);
 }
 
-extern "C" int ecb200_knn_tc_xyz(const void* arow, const void* brow, const float* xxs, int B, int N, int k,
-                                 int32_t* idx, long long* timeline, void* stream) {
-  ECB_REQUIRE(arow && brow && xxs && idx, "ecb200_knn_tc_xyz: null pointer");
+extern "C" int ecb200_knn_tc_xyz(const void* arow, const void* brow, const float* xxs, const float* cmax, int B,
+                                 int N, int k, int32_t* idx, long long* timeline, void* stream) {
+  ECB_REQUIRE(arow && brow && xxs && cmax && idx, "ecb200_knn_tc_xyz: null pointer");
   ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1, "ecb200_knn_tc_xyz: bad shape B=%d N=%d", B, N);
   ECB_REQUIRE(k >= 1 && k <= N, "ecb200_knn_tc_xyz: k=%d out of range for N=%d (selected index k out of range)", k, N);
   ECB_REQUIRE(k <= KMAX, "ecb200_knn_tc_xyz: k=%d exceeds %d (use ecb200_knn)", k, KMAX);
   const float* a_ = static_cast<const float*>(arow);
   const float* b_ = static_cast<const float*>(brow);
   if (tc2_takes(KB, N, k, 1)) {
-    Tc2Args a2 = {a_, a_, b_, b_, xxs, (long long)B * N, B, KB, N, k, 1, idx, timeline};
+    Tc2Args a2 = {a_, a_, b_, b_, nullptr, xxs, cmax, (long long)B * N, B, KB, N, k, 1, idx, timeline};
     return launch_knn_tc2(a2, 1, (cudaStream_t)stream);
   }
   TcArgs a = {a_, a_, b_, b_, xxs, (long long)B * N, B, KB, N, N, k, idx, nullptr, timeline};
   a.ksteps = 1;
+  a.cmax = cmax;
   return launch_knn_f16<1>(a, (cudaStream_t)stream);
 }
 
-extern "C" int ecb200_debug_tc_scores_f16(const void* hh, const void* hl, const float* xxs, int B, int C,
-                                          int N, float* scores, void* stream) {
-  ECB_REQUIRE(hh && hl && xxs && scores, "ecb200_debug_tc_scores_f16: null pointer");
+// diagnostic: the folded contraction itself, s^2 (x_i.x_j - 0.5 |x_j|^2), through the selection kernel's MMA
+// sequence is not observable; this entry multiplies hi/lo only (no norm block) and returns s^2 x_i.x_j
+extern "C" int ecb200_debug_tc_scores_f16(const void* hh, const void* hl, int B, int C, int N, float* scores,
+                                          void* stream) {
+  ECB_REQUIRE(hh && hl && scores, "ecb200_debug_tc_scores_f16: null pointer");
   ECB_REQUIRE(B >= 1 && B <= 65535 && N >= 1, "ecb200_debug_tc_scores_f16: bad shape");
-  ECB_REQUIRE(C % 64 == 0 && C >= 64 && C <= 2 * KB * MAX_KB,
-              "ecb200_debug_tc_scores_f16: C=%d must be a multiple of 64 in [64, 256]", C);
+  ECB_REQUIRE(C == 64 || C == 128, "ecb200_debug_tc_scores_f16: C=%d must be 64 or 128", C);
   const float* h = static_cast<const float*>(hh);
   const float* l = static_cast<const float*>(hl);
-  TcArgs a = {h, l, h, l, xxs, (long long)B * N, B, C / 2, N, N, 1, nullptr, scores, nullptr};
+  TcArgs a = {h, l, h, l, nullptr, (long long)B * N, B, C / 2, N, N, 1, nullptr, scores, nullptr};
   return launch_tc<true, 1, 5, 0, true, 3>(a, (cudaStream_t)stream);
 }
 

@@ -53,12 +53,11 @@ constexpr int S = 5;                          // ring stages
 constexpr int CH = 9;                         // own entries per sweep of the ranking
 
 struct SharedTail {
-  float hx[NG][2][BN];            // [group][ping-pong] -0.5*|x_j|^2 of the current column tile
   int cnt_x[NG][NUM_EPI];         // survivor counts, exchanged between the two threads of a row
   int sum_x[NG][NUM_EPI];         // sums of score-only ranks (tie detection)
-  float xmax_w[NG * 4];           // per-warp max |x_j|^2 over the candidates it staged
   uint64_t a_full, b_full[S], b_empty[S], t_full[NG], t_empty[NG];
   uint32_t tmem_slot;
+  float cmax_s[NRT];              // the cloud's max |s x_j|^2, one copy per row-tile pair
 };
 
 constexpr size_t SURV_BYTES = (size_t)CAP * LS * sizeof(uint64_t);
@@ -68,11 +67,14 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 // TERMS: 3 = hi.hi + hi.lo + lo.hi (the first sweep ranks with hi.hi and a margin); 1 = the hi arrays
 // carry the whole product in one K step (xyz layer), both sweeps issue the same MMA, no margin.
+// The column term -0.5*|x_j|^2 is always part of the contraction (FOLD of knn_tc.cu): with TERMS = 3 one
+// more K step per tile whose candidate rows come from `map_bn`, with TERMS = 1 three slots of the one step.
 template <int TERMS>
 __global__ void __launch_bounds__(NT, 1)
 knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g,
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-               const float* __restrict__ xx, int N, int nkb, int ksteps, int k,
+               const __grid_constant__ CUtensorMap map_bn, const float* __restrict__ xx,
+               const float* __restrict__ cmax_g, int N, int nkb, int ksteps, int k,
                int32_t* __restrict__ idx, long long* tl) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -87,6 +89,7 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
   const int nct = (N + BN - 1) / BN;
   const int cloud_row0 = b * N;
   const int kpa = (nkb & 1) ? 1 : 2;          // hi K-blocks per stage in a single-term sweep
+  const uint32_t A_PER_TILE = (uint32_t)(2 * C + (TERMS == 3 ? UMMA_K : 0));   // TMEM columns of a query tile: hi | lo | 2^15 constants
 
   // epilogue threads fetch their query row before anything else
   float4 pre[16];
@@ -141,18 +144,40 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
           advance();
         }
     };
-    hi_sweep();
     if (TERMS == 1) {
       hi_sweep();
+      hi_sweep();
     } else {
+      // first sweep: nkb hi K-blocks + the norm block of every tile, two blocks per stage
       for (int ct = 0; ct < nct; ++ct)
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int u0 = 0; u0 <= nkb; u0 += 2) {
+          const int nun = min(2, nkb + 1 - u0);
           mbar_wait(&T->b_empty[stage], phase ^ 1);
           if (elect_one_sync()) {
             unsigned char* dst = b_st + (size_t)stage * STAGE_BYTES;
-            mbar_expect_tx(&T->b_full[stage], 2 * TILE_BYTES);
-            tma_load_2d(dst, &map_bhi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
-            tma_load_2d(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+            mbar_expect_tx(&T->b_full[stage], nun * TILE_BYTES);
+            for (int j = 0; j < nun; ++j) {
+              if (u0 + j < nkb) tma_load_2d(dst + j * TILE_BYTES, &map_bhi, &T->b_full[stage], (u0 + j) * KB, cloud_row0 + ct * BN);
+              else              tma_load_2d(dst + j * TILE_BYTES, &map_bn, &T->b_full[stage], 0, cloud_row0 + ct * BN);
+            }
+          }
+          __syncwarp();
+          advance();
+        }
+      // second sweep: (hi | lo) per K-block, then the norm block in a stage of its own
+      for (int ct = 0; ct < nct; ++ct)
+        for (int kb = 0; kb <= nkb; ++kb) {
+          mbar_wait(&T->b_empty[stage], phase ^ 1);
+          if (elect_one_sync()) {
+            unsigned char* dst = b_st + (size_t)stage * STAGE_BYTES;
+            if (kb < nkb) {
+              mbar_expect_tx(&T->b_full[stage], 2 * TILE_BYTES);
+              tma_load_2d(dst, &map_bhi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+              tma_load_2d(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+            } else {
+              mbar_expect_tx(&T->b_full[stage], TILE_BYTES);
+              tma_load_2d(dst, &map_bn, &T->b_full[stage], 0, cloud_row0 + ct * BN);
+            }
           }
           __syncwarp();
           advance();
@@ -170,53 +195,81 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
     const uint32_t ring_lo = sw128_kmajor_desc_lo(smem_u32(b_st));
     constexpr uint32_t STAGE_STEP = STAGE_BYTES >> 4, LO_STEP = TILE_BYTES >> 4, K8_STEP = (UMMA_K * 4) >> 4;
     const uint32_t a_col = tbase + A_COL0;
-    auto sweep = [&](auto three_tag) {
-      constexpr bool three = decltype(three_tag)::value;
-      const int step = three ? 1 : kpa;
-      for (int ct = 0; ct < nct; ++ct, ++tile) {
-        const int as = tile & 1;
-        const uint32_t par = ((tile >> 1) & 1) ^ 1;
-        mbar_wait(&T->t_empty[as], par);        // both row tiles' groups of this parity drained the stage
-        mbar_wait(&T->t_empty[2 + as], par);
-        tc_fence_after();
-        for (int kb = 0; kb < nkb; kb += step) {
-          mbar_wait(&T->b_full[stage], phase);
-          tc_fence_after();
-          const uint32_t bh = ring_lo + (uint32_t)stage * STAGE_STEP;
-          if (elect_one_sync()) {
+    // one stage of a tile: `fn(R, d, aR)` issues that stage's MMAs for row tile R; `last` = the tile's
+    // accumulators are complete after it
+    auto run_stage = [&](int as, bool last, auto fn) {
+      mbar_wait(&T->b_full[stage], phase);
+      tc_fence_after();
+      const uint32_t bh = ring_lo + (uint32_t)stage * STAGE_STEP;
+      if (elect_one_sync()) {
 #pragma unroll
-            for (int R = 0; R < NRT; ++R) {
-              const uint32_t d = tbase + (uint32_t)((R * 2 + as) * BN);
-              const uint32_t aR = a_col + (uint32_t)(R * 2 * C);     // hi halves of row tile R; lo at +C
-              if (three) {
-                const uint32_t ah = aR + (uint32_t)(kb * KB);
-#pragma unroll
-                for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
-                  mma_f16_ts_lo(d, ah + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, (kb | k8) != 0);
-                  mma_f16_ts_lo(d, ah + k8 * UMMA_K, bh + LO_STEP + k8 * K8_STEP, idesc, 1);
-                  mma_f16_ts_lo(d, ah + (uint32_t)C + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, 1);
-                }
-              } else {
-                for (int j = 0; j < kpa; ++j) {
-                  const uint32_t ah = aR + (uint32_t)((kb + j) * KB);
-#pragma unroll
-                  for (int k8 = 0; k8 < KB / UMMA_K; ++k8)
-                    if (k8 < ksteps)
-                      mma_f16_ts_lo(d, ah + k8 * UMMA_K, bh + j * LO_STEP + k8 * K8_STEP, idesc, (kb | j | k8) != 0);
-                }
-              }
-              if (kb + step >= nkb) mma_commit(&T->t_full[R * 2 + as]);   // this row tile's accumulator is complete
-            }
-            mma_commit(&T->b_empty[stage]);      // the stage is free once these MMAs have read it
-          }
-          __syncwarp();
-          if (++stage == S) { stage = 0; phase ^= 1; }
+        for (int R = 0; R < NRT; ++R) {
+          fn(tbase + (uint32_t)((R * 2 + as) * BN), a_col + (uint32_t)(R * A_PER_TILE), bh);
+          if (last) mma_commit(&T->t_full[R * 2 + as]);   // this row tile's accumulator is complete
         }
+        mma_commit(&T->b_empty[stage]);      // the stage is free once these MMAs have read it
       }
+      __syncwarp();
+      if (++stage == S) { stage = 0; phase ^= 1; }
     };
-    sweep(std::false_type{});
-    if (TERMS == 1) sweep(std::false_type{});
-    else            sweep(std::true_type{});
+    auto begin_tile = [&]() -> int {
+      const int as = tile & 1;
+      const uint32_t par = ((tile >> 1) & 1) ^ 1;
+      mbar_wait(&T->t_empty[as], par);        // both row tiles' groups of this parity drained the stage
+      mbar_wait(&T->t_empty[2 + as], par);
+      tc_fence_after();
+      return as;
+    };
+    if (TERMS == 1) {
+      for (int sw = 0; sw < 2; ++sw)
+        for (int ct = 0; ct < nct; ++ct, ++tile) {
+          const int as = begin_tile();
+          for (int kb = 0; kb < nkb; kb += kpa)
+            run_stage(as, kb + kpa >= nkb, [&](uint32_t d, uint32_t aR, uint32_t bh) {
+              for (int j = 0; j < kpa; ++j)
+#pragma unroll
+                for (int k8 = 0; k8 < KB / UMMA_K; ++k8)
+                  if (k8 < ksteps)
+                    mma_f16_ts_lo(d, aR + (uint32_t)((kb + j) * KB) + k8 * UMMA_K, bh + j * LO_STEP + k8 * K8_STEP, idesc,
+                                  (kb | j | k8) != 0);
+            });
+        }
+    } else {
+      for (int ct = 0; ct < nct; ++ct, ++tile) {       // first sweep: hi.hi + norm
+        const int as = begin_tile();
+        for (int u0 = 0; u0 <= nkb; u0 += 2)
+          run_stage(as, u0 + 2 > nkb, [&](uint32_t d, uint32_t aR, uint32_t bh) {
+            const int nun = min(2, nkb + 1 - u0);
+            for (int j = 0; j < nun; ++j) {
+              if (u0 + j < nkb) {
+#pragma unroll
+                for (int k8 = 0; k8 < KB / UMMA_K; ++k8)
+                  mma_f16_ts_lo(d, aR + (uint32_t)((u0 + j) * KB) + k8 * UMMA_K, bh + j * LO_STEP + k8 * K8_STEP, idesc,
+                                (u0 | j | k8) != 0);
+              } else {
+                mma_f16_ts_lo(d, aR + (uint32_t)(2 * C), bh + j * LO_STEP, idesc, 1);
+              }
+            }
+          });
+      }
+      for (int ct = 0; ct < nct; ++ct, ++tile) {       // second sweep: three terms + norm
+        const int as = begin_tile();
+        for (int kb = 0; kb <= nkb; ++kb)
+          run_stage(as, kb == nkb, [&](uint32_t d, uint32_t aR, uint32_t bh) {
+            if (kb < nkb) {
+              const uint32_t ah = aR + (uint32_t)(kb * KB);
+#pragma unroll
+              for (int k8 = 0; k8 < KB / UMMA_K; ++k8) {
+                mma_f16_ts_lo(d, ah + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, (kb | k8) != 0);
+                mma_f16_ts_lo(d, ah + k8 * UMMA_K, bh + LO_STEP + k8 * K8_STEP, idesc, 1);
+                mma_f16_ts_lo(d, ah + (uint32_t)C + k8 * UMMA_K, bh + k8 * K8_STEP, idesc, 1);
+              }
+            } else {
+              mma_f16_ts_lo(d, aR + (uint32_t)(2 * C), bh, idesc, 1);
+            }
+          });
+      }
+    }
   } else {
     // ===================== epilogue: selection (thread = query row x tile parity) =====================
     const int g = (warp - 2) >> 2;      // warpgroup
@@ -226,11 +279,10 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
     const int row = rt * BM + R * RT + q * 32 + lane;
     const bool valid = row < N;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN);
-    auto group_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(NUM_EPI) : "memory"); };
     auto pair_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(5 + R), "n"(2 * NUM_EPI) : "memory"); };
     {
       // query rows -> tensor memory: parity 0 copies the hi halves, parity 1 the lo halves of its row tile
-      const uint32_t dst = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + (uint32_t)(R * 2 * C + p * C);
+      const uint32_t dst = tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + (uint32_t)R * A_PER_TILE + (uint32_t)(p * C);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (h * 32 < C) {
@@ -245,9 +297,25 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
           tmem_st_32x32(dst + (uint32_t)(h * 32), r);
         }
       }
+      if (TERMS == 3 && p == 0) {
+        // the query side of the norm block: 2^15 (0x7800) in its first three K slots, the same for every row
+        uint32_t r[8] = {0x78007800u, 0x00007800u, 0u, 0u, 0u, 0u, 0u, 0u};
+        __syncwarp();
+        tmem_st_32x8(tmem_base + ((uint32_t)(q * 32) << 16) + A_COL0 + (uint32_t)R * A_PER_TILE + (uint32_t)(2 * C), r);
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&T->a_full);
+    }
+    if (p == 0 && et < 32) {
+      // the cloud's largest squared norm from the per-block maxima of the operand kernel (read by the
+      // pair's threads after the pair barrier of the threshold stage)
+      const int nblk = (N + 31) / 32;
+      float m = 0.f;
+      for (int i = lane; i < nblk; i += 32) m = fmaxf(m, __ldg(cmax_g + (size_t)b * nblk + i));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) T->cmax_s[R] = m;
     }
     float bin[NB];
 #pragma unroll
@@ -259,43 +327,23 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
     constexpr uint32_t SLOT = LS * sizeof(uint64_t);
     const float xi = valid ? __ldg(xx + cloud_row0 + row) : 0.f;
     float thr = CUDART_INF_F;
-    float xmax = 0.f;
-    int use = 0;
-    // |x_j|^2 of column `et` of candidate tile t (threads et < BN stage it); -1 marks a column past the cloud
-    auto load_xx = [&](int t) -> float {
-      const int j = t * BN + et;
-      return (et < BN && j < N) ? __ldg(xx + cloud_row0 + j) : -1.f;
-    };
-    int xnext_t = p;
-    float xnext = load_xx(xnext_t);
+    int use = 0;  // how many times this group has consumed its accumulator stage
     auto run_tiles = [&](auto pass_tag) {
       constexpr int pass = decltype(pass_tag)::value;
       const int tile0 = pass * nct;
       for (int ct = (tile0 + p) & 1; ct < nct; ct += 2, ++use) {
-        float* hx = T->hx[g][use & 1];
-        {
-          if (xnext_t != ct) xnext = load_xx(ct);
-          const float xj = xnext;
-          int nct_t = ct + 2;
-          if (nct_t >= nct) nct_t = ((pass + 1) * nct + p) & 1;
-          xnext = load_xx(nct_t);
-          xnext_t = nct_t;
-          xmax = fmaxf(xmax, xj);
-          if (et < BN) hx[et] = (xj >= 0.f) ? -0.5f * xj : -CUDART_INF_F;
-        }
-        group_bar();
         mbar_wait(&T->t_full[g], use & 1);
         tc_fence_after();
         auto process = [&](uint32_t(&cur)[32], const int c2, const bool second_pass) {
-          const float4* hx4 = reinterpret_cast<const float4*>(hx + c2 * 32);
+          // the accumulator already is the score; only the ragged last tile needs the columns past the
+          // end of the cloud masked (warp-uniform branch)
           float v[32];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 h4 = hx4[e];
-            v[4 * e + 0] = __uint_as_float(cur[4 * e + 0]) + h4.x;
-            v[4 * e + 1] = __uint_as_float(cur[4 * e + 1]) + h4.y;
-            v[4 * e + 2] = __uint_as_float(cur[4 * e + 2]) + h4.z;
-            v[4 * e + 3] = __uint_as_float(cur[4 * e + 3]) + h4.w;
+          for (int u = 0; u < 32; ++u) v[u] = __uint_as_float(cur[u]);
+          if ((ct + 1) * BN > N) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+              if (ct * BN + c2 * 32 + u >= N) v[u] = -CUDART_INF_F;
           }
           if (!second_pass) {
 #pragma unroll
@@ -358,9 +406,6 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
     // max_i min(mine[i-1], theirs[k-i-1]).  The partner's list travels through the (still empty)
     // survivor area, written reversed so that the reader walks it with static offsets.
     float* exch = reinterpret_cast<float*>(surv);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-    if (lane == 0) T->xmax_w[warp - 2] = xmax;
     {
       float* wr = exch + (size_t)(k - 1) * LS + me;     // slot k-1-u  <-  bin[u]
 #pragma unroll
@@ -378,9 +423,7 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
         tau = fmaxf(tau, fminf(mine, theirs));
       }
     }
-    float cmax = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) cmax = fmaxf(cmax, T->xmax_w[R * 8 + w]);
+    const float cmax = T->cmax_s[R];
     // first sweep scored with hi.hi only: lower the bound by the rigorous margin of knn_tc.cu
     float margin = 1.1f * 0.0009765625f * sqrtf(xi * cmax) + 1e-30f;
     margin += 5.96e-8f * sqrtf((float)(2 * C)) * (sqrtf(xi) + sqrtf(cmax));
@@ -492,12 +535,18 @@ int launch(const ecb200::knntc::Tc2Args& a, cudaStream_t st) {
   OperandMaps Bm;
   int rc = make_operand(&Bm, a.b_hi, a.b_lo, a.b_rows, a.Cw, BN);
   if (rc) return rc;
+  CUtensorMap Bn = Bm.hi;   // placeholder unless the norm block is a separate operand
+  if (TERMS == 3) {
+    rc = make_point_map(&Bn, a.bn, a.b_rows, KB, BN);
+    if (rc) return rc;
+  }
   auto kern = knn_tc2_kernel<TERMS>;
   static thread_local bool seen[ecb200::kMaxDevices] = {};
   if (ecb200::first_use_on_device(seen))
     ECB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   dim3 grid(ecb200::ceil_div(a.N, BM), a.clouds);
-  kern<<<grid, NT, SMEM_BYTES, st>>>(a.a_hi, a.a_lo, Bm.hi, Bm.lo, a.xx, a.N, a.Cw / KB, a.ksteps, a.k, a.idx, a.tl);
+  kern<<<grid, NT, SMEM_BYTES, st>>>(a.a_hi, a.a_lo, Bm.hi, Bm.lo, Bn, a.xx, a.cmax, a.N, a.Cw / KB, a.ksteps, a.k,
+                                     a.idx, a.tl);
   ECB_LAUNCH_CHECK("knn_tc2_kernel");
   return ECB200_OK;
 }
@@ -514,7 +563,9 @@ namespace knntc {
 bool tc2_takes(int Cw, int N, int k, int terms) {
   const char* e = getenv("ECB200_KNN_ROWS");
   const int rows = e ? atoi(e) : 0;
-  if (!(k <= KMAX && Cw % KB == 0 && Cw >= KB && Cw <= 2 * KB && N > RT)) return false;
+  // tensor memory: 4 x 64 accumulator columns + two query tiles of 2 Cw (+ 8 constants): three-term
+  // products fit for Cw = 32 (64 channels) only
+  if (!(k <= KMAX && N > RT && (Cw == KB || (Cw == 2 * KB && terms == 1)))) return false;
   if (rows == 128) return false;
   if (rows == 256) return true;
   return terms == 1;

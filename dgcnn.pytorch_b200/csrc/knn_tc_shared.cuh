@@ -115,7 +115,7 @@ inline int make_operand(OperandMaps* m, const float* hi, const float* lo, long l
 
 // 256-row variant (knn_tc2.cu): packed-FP16 operands, Cw = 32-bit words per operand row
 struct Tc2Args {
-  const float *a_hi, *a_lo, *b_hi, *b_lo, *xx;
+  const float *a_hi, *a_lo, *b_hi, *b_lo, *bn, *xx, *cmax;   // bn: norm rows (TERMS = 3) or NULL
   long long b_rows;
   int clouds, Cw, N, k, ksteps;
   int32_t* idx;

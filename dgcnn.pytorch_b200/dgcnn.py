@@ -101,8 +101,8 @@ def edgeconv_block(x: torch.Tensor, block: nn.Sequential, k: int,
         if idx is None and ops.knn_tc_kind(C, N, int(k)) == "f16":
             # one pass over x makes the packed fp16 halves of the kNN and the tf32 halves of the GEMMs
             gemm_tc = ops.point_gemm_uses_tensor_cores(C)
-            hh, hl, xxs, xhi, xlo, _ = ops.split_f16_op(x.detach().contiguous(), gemm_tc, ops.known_amax(x))
-            idx = ops.knn_tc_f16_op(hh, hl, xxs, B, N, int(k))
+            hh, hl, nb, xxs, cmax, xhi, xlo, _ = ops.split_f16_op(x.detach().contiguous(), gemm_tc, ops.known_amax(x))
+            idx = ops.knn_tc_f16_op(hh, hl, nb, xxs, cmax, B, N, int(k))
             if not gemm_tc:
                 xhi = xlo = None
         else:

@@ -132,8 +132,8 @@ def knn_op(x: Tensor, k: int, sorted: bool = True) -> Tensor:
     kind = knn_tc_kind(C, N, k)
     if kind == "f16":
         # feature-space layers: tcgen05 / TMA distance tiles (knn_tc.cu), packed fp16 halves
-        hh, hl, xxs = split_f16_op(x, False)[:3]
-        return knn_tc_f16_op(hh, hl, xxs, B, N, k)
+        hh, hl, nb, xxs, cmax = split_f16_op(x, False)[:5]
+        return knn_tc_f16_op(hh, hl, nb, xxs, cmax, B, N, k)
     if kind == "tf32":
         hi, lo, xx = split_tf32_op(x)
         return knn_tc_op(hi, lo, xx, B, N, k)
@@ -193,9 +193,11 @@ def _(hi, lo, xx, B, N, k):
 # ---- packed-FP16 operands (kind::f16): same 11-bit significands as tf32 at twice the MMA rate ----
 @torch.library.custom_op("edgeconv_b200::split_f16", mutates_args=(), device_types="cuda")
 def split_f16_op(x: Tensor, with_tf32: bool, amax: Optional[Tensor] = None) -> List[Tensor]:
-    """x [B,C,N] -> [hh, hl (fp16 [B*N,C]), xxs [B*N], hi, lo (tf32-valued fp32 [B*N,C]), xx [B*N]].
-    hh/hl/xxs are the operands of knn_tc_f16_op (the tensor scaled by a power of two into fp16's
-    range); hi/lo/xx those of the tensor-core GEMMs, from the same pass (empty unless with_tf32).
+    """x [B,C,N] -> [hh, hl (fp16 [B*N,C]), nb (fp16 [B*N,64]), xxs [B*N], cmax [B], hi, lo (tf32-valued
+    fp32 [B*N,C]), xx [B*N]].  hh/hl/nb/xxs/cmax are the operands of knn_tc_f16_op (the tensor scaled by a
+    power of two into fp16's range; nb = the candidate rows of the folded -0.5|x_j|^2 term, cmax = the
+    clouds' largest scaled squared norms); hi/lo/xx those of the tensor-core GEMMs, from the same pass
+    (empty unless with_tf32).
     ``amax`` [AMAX_SLOTS]: max |x| when the producer of x already knows it (ecb200_edge_apply_amax)."""
     _check_cuda_f32("x", x, 3)
     B, C, N = x.shape
@@ -205,7 +207,9 @@ def split_f16_op(x: Tensor, with_tf32: bool, amax: Optional[Tensor] = None) -> L
         st = _stream(x)
         hh = torch.empty(B * N, C, device=dev, dtype=torch.float16)
         hl = torch.empty(B * N, C, device=dev, dtype=torch.float16)
+        nb = torch.empty(B * N, 64, device=dev, dtype=torch.float16)
         xxs = torch.empty(B * N, device=dev, dtype=torch.float32)
+        cmax = torch.empty(B * ((N + 31) // 32), device=dev, dtype=torch.float32)
         hi = lo = xx = None
         if with_tf32:
             hi = torch.empty(B * N, C, device=dev, dtype=torch.float32)
@@ -214,11 +218,11 @@ def split_f16_op(x: Tensor, with_tf32: bool, amax: Optional[Tensor] = None) -> L
         if amax is None:
             amax = torch.empty(AMAX_SLOTS, device=dev, dtype=torch.float32)
             _lib.call("ecb200_absmax", _ptr(x), x.numel(), _ptr(amax), st)
-        _lib.call("ecb200_split_f16", _ptr(x), B, C, N, _ptr(amax), _ptr(hh), _ptr(hl), _ptr(xxs),
-                  _ptr(hi), _ptr(lo), _ptr(xx), st)
+        _lib.call("ecb200_split_f16", _ptr(x), B, C, N, _ptr(amax), _ptr(hh), _ptr(hl), _ptr(nb), _ptr(xxs),
+                  _ptr(cmax), _ptr(hi), _ptr(lo), _ptr(xx), st)
     if not with_tf32:
         hi, lo, xx = xxs.new_empty(0), xxs.new_empty(0), xxs.new_empty(0)
-    return [hh, hl, xxs, hi, lo, xx]
+    return [hh, hl, nb, xxs, cmax, hi, lo, xx]
 
 
 @split_f16_op.register_fake
@@ -227,24 +231,26 @@ def _(x, with_tf32, amax=None):
     h = x.new_empty((B * N, C), dtype=torch.float16)
     f = x.new_empty((B * N, C)) if with_tf32 else x.new_empty(0)
     v = x.new_empty((B * N,)) if with_tf32 else x.new_empty(0)
-    return [h, x.new_empty((B * N, C), dtype=torch.float16), x.new_empty((B * N,)), f,
+    return [h, x.new_empty((B * N, C), dtype=torch.float16), x.new_empty((B * N, 64), dtype=torch.float16),
+            x.new_empty((B * N,)), x.new_empty((B * ((N + 31) // 32),)), f,
             x.new_empty((B * N, C)) if with_tf32 else x.new_empty(0), v]
 
 
 @torch.library.custom_op("edgeconv_b200::knn_tc_f16", mutates_args=(), device_types="cuda")
-def knn_tc_f16_op(hh: Tensor, hl: Tensor, xxs: Tensor, B: int, N: int, k: int) -> Tensor:
+def knn_tc_f16_op(hh: Tensor, hl: Tensor, nb: Tensor, xxs: Tensor, cmax: Tensor, B: int, N: int, k: int) -> Tensor:
     """kNN graph from the packed fp16 operands: int32 [B,N,k], nearest first."""
     C = hh.shape[1]
     if k > N or k < 1:
         raise RuntimeError(f"selected index k out of range (k={k}, N={N})")
     with torch.cuda.device(hh.device):
         idx = torch.empty(B, N, k, device=hh.device, dtype=torch.int32)
-        _lib.call("ecb200_knn_tc_f16", _ptr(hh), _ptr(hl), _ptr(xxs), B, C, N, k, _ptr(idx), None, _stream(hh))
+        _lib.call("ecb200_knn_tc_f16", _ptr(hh), _ptr(hl), _ptr(nb), _ptr(xxs), _ptr(cmax), B, C, N, k, _ptr(idx),
+                  None, _stream(hh))
     return idx
 
 
 @knn_tc_f16_op.register_fake
-def _(hh, hl, xxs, B, N, k):
+def _(hh, hl, nb, xxs, cmax, B, N, k):
     return hh.new_empty((B, N, k), dtype=torch.int32)
 
 
@@ -262,9 +268,11 @@ def knn_tc_xyz_op(x: Tensor, k: int) -> Tensor:
         st = _stream(x)
         rows = torch.empty(2, B * N, 64, device=dev, dtype=torch.float16)
         xxs = torch.empty(B * N, device=dev, dtype=torch.float32)
+        cmax = torch.empty(B * ((N + 31) // 32), device=dev, dtype=torch.float32)
         idx = torch.empty(B, N, k, device=dev, dtype=torch.int32)
-        _lib.call("ecb200_pack_xyz_f16", _ptr(x), B, C, N, _ptr(rows[0]), _ptr(rows[1]), _ptr(xxs), st)
-        _lib.call("ecb200_knn_tc_xyz", _ptr(rows[0]), _ptr(rows[1]), _ptr(xxs), B, N, k, _ptr(idx), None, st)
+        _lib.call("ecb200_pack_xyz_f16", _ptr(x), B, C, N, _ptr(rows[0]), _ptr(rows[1]), _ptr(xxs), _ptr(cmax), st)
+        _lib.call("ecb200_knn_tc_xyz", _ptr(rows[0]), _ptr(rows[1]), _ptr(xxs), _ptr(cmax), B, N, k, _ptr(idx),
+                  None, st)
     return idx
 
 
@@ -275,15 +283,15 @@ def _(x, k):
 
 
 def knn_tc_kind(C: int, N: int, k: int) -> str:
-    """Which tensor-core kernel knn() uses: "f16" (packed fp16 halves, C a multiple of 64), "tf32"
-    (C a multiple of 32), "xyz" (C <= 5, N >= 64) or "" (FP32-FMA kernel).  ECB200_KNN=fma|tf32 and
+    """Which tensor-core kernel knn() uses: "f16" (packed fp16 halves, C = 64 or 128), "tf32"
+    (the other multiples of 32 up to 128), "xyz" (C <= 4, N >= 64) or "" (FP32-FMA kernel).  ECB200_KNN=fma|tf32 and
     ECB200_KNN_XYZ=fma override (A/B tests)."""
     mode = os.environ.get("ECB200_KNN", "auto")
     if mode == "fma" or k > 40:
         return ""
-    if C <= 5:
+    if C <= 4:
         return "xyz" if (N >= 64 and os.environ.get("ECB200_KNN_XYZ", "tc") == "tc") else ""
-    if C % 64 == 0 and 64 <= C <= 256 and mode != "tf32":
+    if C in (64, 128) and mode != "tf32":
         return "f16"
     if C % 32 == 0 and 32 <= C <= 128:
         return "tf32"
@@ -298,25 +306,18 @@ def knn_uses_tensor_cores(C: int, N: int, k: int) -> bool:
 
 
 def debug_tc_scores_f16(x: Tensor) -> Tensor:
-    """Diagnostic: scores x_i.x_j - 0.5|x_j|^2 [B,N,N] from the packed-fp16 pipeline (unscaled)."""
+    """Diagnostic: scores x_i.x_j - 0.5|x_j|^2 [B,N,N] with the dot products from the packed-fp16
+    three-term pipeline (unscaled; the column term is added here in fp64-free torch arithmetic)."""
     _check_cuda_f32("x", x, 3)
     B, C, N = x.shape
     x = x.contiguous()
     with torch.cuda.device(x.device):
-        amax = torch.empty(AMAX_SLOTS, device=x.device, dtype=torch.float32)
-        hh = torch.empty(B * N, C, device=x.device, dtype=torch.float16)
-        hl = torch.empty_like(hh)
-        xxs = torch.empty(B * N, device=x.device, dtype=torch.float32)
+        hh, hl, nb, xxs, cmax = split_f16_op(x, False)[:5]
         out = torch.full((B, N, N), float("nan"), device=x.device, dtype=torch.float32)
-        st = _stream(x)
-        _lib.call("ecb200_absmax", _ptr(x), x.numel(), _ptr(amax), st)
-        _lib.call("ecb200_split_f16", _ptr(x), B, C, N, _ptr(amax), _ptr(hh), _ptr(hl), _ptr(xxs), None, None,
-                  None, st)
-        _lib.call("ecb200_debug_tc_scores_f16", _ptr(hh), _ptr(hl), _ptr(xxs), B, C, N, _ptr(out), st)
-        import math
-        e = math.frexp(float(amax.max()))[1] if float(amax.max()) > 0 else 14
-        s = 2.0 ** (14 - e)
-    return out / (s * s)
+        _lib.call("ecb200_debug_tc_scores_f16", _ptr(hh), _ptr(hl), B, C, N, _ptr(out), _stream(x))
+        xx = (x.double() ** 2).sum(1)
+        s2 = (xxs.view(B, N).double().sum() / xx.sum().clamp_min(1e-300)).item() if float(xx.sum()) > 0 else 1.0
+    return (out.double() / s2 - 0.5 * xx[:, None, :]).float()
 
 
 def debug_tc_scores(x: Tensor) -> Tensor:

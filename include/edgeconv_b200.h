@@ -97,31 +97,38 @@ int ecb200_debug_tc_scores(const float* hi, const float* lo, const float* xx, in
                            float* scores, void* stream);
 /* The same kNN with packed FP16 operands (tcgen05 kind::f16): fp16 and tf32 carry the same 11-bit
  * significand, so the compensated product hi.hi + hi.lo + lo.hi is as accurate as 3xTF32 once the
- * tensor has been moved into fp16's range by a power of two -- at twice the tensor-pipe rate.
+ * tensor has been moved into fp16's range by a power of two -- at twice the tensor-pipe rate.  The
+ * column term -0.5|x_j|^2 is part of the contraction (three more K slots: 2^15 on the query side, the
+ * three fp16 pieces of -|s x_j|^2 / 2^16 on the candidate side), so the accumulator IS the score.
  *   ecb200_absmax:       max_s amax[s] = max |x| over n values; amax has ECB200_AMAX_SLOTS floats
  *                        (several slots, so that thousands of blocks do not hammer one address; the
  *                        callee zero-fills them first, consumers take the maximum over the slots)
- *   ecb200_split_f16:    s = 2^(14 - exponent(amax)); hh = fp16(s x), hl = fp16(s x - hh), point-major
- *                        [B*N, C] halves (C even), xxs[B*N] = s^2 |x|^2; optionally (hi/lo/xx non-NULL)
- *                        the outputs of ecb200_split_tf32 from the same pass over x
- *   ecb200_knn_tc_f16:   idx as ecb200_knn (nearest first); C a multiple of 64 in [64,256], k <= 40;
+ *   ecb200_split_f16:    s = 2^(12 - exponent(amax)); point-major halves hh = fp16(s x), hl = fp16(s x - hh)
+ *                        [B*N, C] (C even, <= 128); nb [B*N, 64] halves = the norm block's candidate rows
+ *                        (three pieces + zeros in the first 32 bytes of a 128-byte row); xxs[B*N] = s^2|x|^2;
+ *                        cmax[B, ceil(N/32)] = max of xxs over each 32 points (the kNN kernels reduce
+ *                        them to the cloud's maximum: no atomics, no zero-fill); optionally
+ *                        (hi/lo/xx non-NULL) the outputs of ecb200_split_tf32 from the same pass over x
+ *   ecb200_knn_tc_f16:   idx as ecb200_knn (nearest first); C = 64 or 128, k <= 40;
  *                        `timeline` NULL, or the diagnostic buffer of ecb200_debug_tc_timeline
- *   ecb200_pack_xyz_f16 / ecb200_knn_tc_xyz: the xyz layer (C <= 5) on the same pipeline -- the three
- *                        terms of a point's compensated product sit side by side in ONE 16-deep K
- *                        step (query rows [h|h|l], candidate rows [h|l|h], 128-byte rows), one MMA
- *                        per 128 x 128 tile and sweep; the scale is per cloud, found by the pack kernel
- *   ecb200_debug_tc_scores_f16: diagnostic -- s^2 (x_i.x_j - 0.5|x_j|^2) [B,N,N] */
+ *   ecb200_pack_xyz_f16 / ecb200_knn_tc_xyz: the xyz layer (C <= 4) on the same pipeline -- the three
+ *                        terms of a point's compensated product AND the norm term sit side by side in
+ *                        ONE 16-deep K step (query rows [h|h|l|2^15 x3], candidate rows [h|l|h|pieces],
+ *                        128-byte rows), one MMA per tile and sweep; the scale is per cloud, found by
+ *                        the pack kernel, which also writes cmax[B, ceil(N/32)]
+ *   ecb200_debug_tc_scores_f16: diagnostic -- s^2 x_i.x_j [B,N,N] from the hi/lo halves */
 int ecb200_absmax(const float* x, long long n, float* amax, void* stream);
 int ecb200_split_f16(const float* x, int B, int C, int N, const float* amax, void* hh, void* hl,
-                     float* xxs, float* hi, float* lo, float* xx, void* stream);
-int ecb200_knn_tc_f16(const void* hh, const void* hl, const float* xxs, int B, int C, int N, int k,
-                      int32_t* idx, long long* timeline, void* stream);
+                     void* nb, float* xxs, float* cmax, float* hi, float* lo, float* xx, void* stream);
+int ecb200_knn_tc_f16(const void* hh, const void* hl, const void* nb, const float* xxs,
+                      const float* cmax, int B, int C, int N, int k, int32_t* idx, long long* timeline,
+                      void* stream);
 int ecb200_pack_xyz_f16(const float* x, int B, int C, int N, void* arow, void* brow, float* xxs,
-                        void* stream);
-int ecb200_knn_tc_xyz(const void* arow, const void* brow, const float* xxs, int B, int N, int k,
-                      int32_t* idx, long long* timeline, void* stream);
-int ecb200_debug_tc_scores_f16(const void* hh, const void* hl, const float* xxs, int B, int C,
-                               int N, float* scores, void* stream);
+                        float* cmax, void* stream);
+int ecb200_knn_tc_xyz(const void* arow, const void* brow, const float* xxs, const float* cmax, int B,
+                      int N, int k, int32_t* idx, long long* timeline, void* stream);
+int ecb200_debug_tc_scores_f16(const void* hh, const void* hl, int B, int C, int N, float* scores,
+                               void* stream);
 /* hi = tf32(src), lo = tf32(src - hi), element-wise over n values (operand prep for the
  * tensor-core GEMM: Wcat is already K-major) */
 int ecb200_split_rows_tf32(const float* src, long long n, float* hi, float* lo, void* stream);

@@ -95,18 +95,20 @@ def test_argument_validation_of_the_newer_entry_points(ec):
 def test_argument_validation_of_the_fp16_knn_entry_points(ec):
     one = ctypes.c_void_p(16)
     call = ec._lib.call
-    with pytest.raises(RuntimeError, match="multiple of 64"):
-        call("ecb200_knn_tc_f16", one, one, one, 1, 96, 256, 8, one, None, None)
+    with pytest.raises(RuntimeError, match="must be 64 or 128"):
+        call("ecb200_knn_tc_f16", one, one, one, one, one, 1, 96, 256, 8, one, None, None)
     with pytest.raises(RuntimeError, match="out of range"):
-        call("ecb200_knn_tc_f16", one, one, one, 1, 64, 16, 20, one, None, None)
+        call("ecb200_knn_tc_f16", one, one, one, one, one, 1, 64, 16, 20, one, None, None)
     with pytest.raises(RuntimeError, match="exceeds 40"):
-        call("ecb200_knn_tc_xyz", one, one, one, 1, 256, 41, one, None, None)
-    with pytest.raises(RuntimeError, match="C <= 5"):
-        call("ecb200_pack_xyz_f16", one, 1, 6, 64, one, one, one, None)
+        call("ecb200_knn_tc_xyz", one, one, one, one, 1, 256, 41, one, None, None)
+    with pytest.raises(RuntimeError, match="C <= 4"):
+        call("ecb200_pack_xyz_f16", one, 1, 5, 64, one, one, one, one, None)
     with pytest.raises(RuntimeError, match="C must be even"):
-        call("ecb200_split_f16", one, 1, 7, 64, one, one, one, one, None, None, None, None)
+        call("ecb200_split_f16", one, 1, 7, 64, one, one, one, one, one, one, None, None, None, None)
+    with pytest.raises(RuntimeError, match="at most 128"):
+        call("ecb200_split_f16", one, 1, 256, 64, one, one, one, one, one, one, None, None, None, None)
     with pytest.raises(RuntimeError, match="come as a pair"):
-        call("ecb200_split_f16", one, 1, 8, 64, one, one, one, one, one, None, None, None)
+        call("ecb200_split_f16", one, 1, 8, 64, one, one, one, one, one, one, one, None, None, None)
     with pytest.raises(RuntimeError, match="bad arguments"):
         call("ecb200_absmax", one, 0, one, None)
     with pytest.raises(RuntimeError, match="null pointer"):
@@ -116,7 +118,7 @@ def test_argument_validation_of_the_fp16_knn_entry_points(ec):
     # one-K-step kernel for xyz-like inputs, FP32 FMA for everything else
     kind = ec.ops.knn_tc_kind
     assert [kind(64, 1024, 20), kind(128, 1024, 40), kind(96, 512, 20), kind(3, 1024, 20), kind(9, 512, 20),
-            kind(64, 512, 41), kind(3, 32, 8)] == ["f16", "f16", "tf32", "xyz", "", "", ""]
+            kind(64, 512, 41), kind(3, 32, 8), kind(5, 512, 8)] == ["f16", "f16", "tf32", "xyz", "", "", "", ""]
 
 
 def test_cpu_tensors_are_rejected_not_served(ec):

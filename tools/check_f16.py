@@ -28,7 +28,7 @@ def exact_scores(x):
 
 
 if what in ("all", "scores"):
-    for (B, C, N, scale) in [(2, 64, 256, 1.0), (1, 128, 384, 1.0), (2, 64, 200, 1e-3), (1, 128, 130, 3e4), (1, 256, 256, 1.0)]:
+    for (B, C, N, scale) in [(2, 64, 256, 1.0), (1, 128, 384, 1.0), (2, 64, 200, 1e-3), (1, 128, 130, 3e4)]:
         x = (orc.synthetic_features(B, C, N, seed=C + N) * scale).to(dev)
         ref = exact_scores(x)
         s16 = ops.debug_tc_scores_f16(x).double()
@@ -43,8 +43,8 @@ if what in ("all", "scores"):
 
 if what in ("all", "parity"):
     cases = [(4, 64, 1024, 20, "feat"), (2, 128, 1024, 20, "feat"), (2, 64, 2048, 40, "feat"), (1, 128, 4096, 20, "feat"),
-             (3, 64, 200, 12, "feat"), (1, 256, 300, 33, "feat"), (32, 3, 1024, 20, "xyz"), (4, 3, 2048, 40, "xyz"),
-             (2, 3, 4096, 20, "xyz"), (3, 3, 333, 16, "xyz"), (5, 3, 64, 40, "xyz"), (2, 5, 100, 7, "feat5")]
+             (3, 64, 200, 12, "feat"), (1, 128, 300, 33, "feat"), (32, 3, 1024, 20, "xyz"), (4, 3, 2048, 40, "xyz"),
+             (2, 3, 4096, 20, "xyz"), (3, 3, 333, 16, "xyz"), (5, 3, 64, 40, "xyz"), (2, 4, 100, 7, "feat4")]
     for B, C, N, k, kind in cases:
         if kind == "xyz":
             x = orc.synthetic_xyz(B, N, seed=B + N)
@@ -82,18 +82,25 @@ def timeit(fn, n=30):
 
 
 if what in ("all", "time"):
+    for rows in ("128", "256"):
+        os.environ["ECB200_KNN_ROWS"] = rows
+        for (B, C, N, k) in [(32, 64, 1024, 20), (32, 3, 1024, 20)]:
+            x = (orc.synthetic_xyz(B, N, seed=1) if C == 3 else orc.synthetic_features(B, C, N, seed=1)).to(dev)
+            t = timeit(lambda: ops.knn_op(x, k, True))
+            print(f"time knn() incl. operand prep, rows/CTA {rows}: B={B} C={C} N={N} k={k}: {t:.1f} us", flush=True)
+    os.environ.pop("ECB200_KNN_ROWS")
     for (B, C, N, k) in [(32, 64, 1024, 20), (32, 128, 1024, 20), (32, 64, 2048, 40), (8, 128, 4096, 20)]:
         x = orc.synthetic_features(B, C, N, seed=1).to(dev)
         st = stream()
-        hh, hl, xxs, hi, lo, xx = ops.split_f16_op(x, True)
+        hh, hl, nb, xxs, cmax, hi, lo, xx = ops.split_f16_op(x, True)
         idx = torch.empty(B, N, k, device=dev, dtype=torch.int32)
         ws = torch.empty(256, device=dev, dtype=torch.uint8)
         amax = torch.empty(32, device=dev)
         fl = 2.0 * B * N * N * C
-        t16 = timeit(lambda: L.call("ecb200_knn_tc_f16", P(hh), P(hl), P(xxs), B, C, N, k, P(idx), None, st))
+        t16 = timeit(lambda: L.call("ecb200_knn_tc_f16", P(hh), P(hl), P(nb), P(xxs), P(cmax), B, C, N, k, P(idx), None, st))
         t32 = timeit(lambda: L.call("ecb200_knn_tc", P(hi), P(lo), P(xx), B, C, N, k, 1, P(idx), P(ws), 256, st))
         tam = timeit(lambda: L.call("ecb200_absmax", P(x), x.numel(), P(amax), st))
-        tsp = timeit(lambda: L.call("ecb200_split_f16", P(x), B, C, N, P(amax), P(hh), P(hl), P(xxs), P(hi), P(lo), P(xx), st))
+        tsp = timeit(lambda: L.call("ecb200_split_f16", P(x), B, C, N, P(amax), P(hh), P(hl), P(nb), P(xxs), P(cmax), P(hi), P(lo), P(xx), st))
         ts0 = timeit(lambda: L.call("ecb200_split_tf32", P(x), B, C, N, P(hi), P(lo), P(xx), st))
         print(f"time B={B} C={C} N={N} k={k}: knn f16 {t16:.1f} us ({fl / t16 / 1e6:.1f} TF/s)  tf32 {t32:.1f} us "
               f"({fl / t32 / 1e6:.1f} TF/s)   absmax {tam:.1f}  split_f16(+tf32) {tsp:.1f}  split_tf32 {ts0:.1f}", flush=True)
@@ -102,10 +109,11 @@ if what in ("all", "time"):
         st = stream()
         rows = torch.empty(2, B * N, 64, device=dev, dtype=torch.float16)
         xxs = torch.empty(B * N, device=dev)
+        cmax = torch.empty(B * ((N + 31) // 32), device=dev)
         idx = torch.empty(B, N, k, device=dev, dtype=torch.int32)
         xx = torch.empty(B * N, device=dev)
-        tpk = timeit(lambda: L.call("ecb200_pack_xyz_f16", P(x), B, 3, N, P(rows[0]), P(rows[1]), P(xxs), st))
-        ttc = timeit(lambda: L.call("ecb200_knn_tc_xyz", P(rows[0]), P(rows[1]), P(xxs), B, N, k, P(idx), None, st))
+        tpk = timeit(lambda: L.call("ecb200_pack_xyz_f16", P(x), B, 3, N, P(rows[0]), P(rows[1]), P(xxs), P(cmax), st))
+        ttc = timeit(lambda: L.call("ecb200_knn_tc_xyz", P(rows[0]), P(rows[1]), P(xxs), P(cmax), B, N, k, P(idx), None, st))
         L.call("ecb200_sqnorms", P(x), B, 3, N, P(xx), st)
         tfm = timeit(lambda: L.call("ecb200_knn", P(x), P(xx), B, 3, N, k, 1, P(idx), st))
         print(f"time xyz B={B} N={N} k={k}: tensor-core {ttc:.1f} us (+ pack {tpk:.1f})   fma kernel {tfm:.1f} us", flush=True)

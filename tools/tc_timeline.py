@@ -42,12 +42,13 @@ P = lambda t: None if t is None else c_void_p(t.data_ptr())
 st = c_void_p(torch.cuda.current_stream().cuda_stream)
 L.call("ecb200_split_tf32", P(x), B, C, N, P(hi), P(lo), P(xx), st)
 if KIND == "f16":
-    hh, hl, xxs = ec.ops.split_f16_op(x, False)[:3]
-    launch = lambda t: L.call("ecb200_knn_tc_f16", P(hh), P(hl), P(xxs), B, C, N, k, P(idx), t, st)
+    hh, hl, nb, xxs, cmax = ec.ops.split_f16_op(x, False)[:5]
+    launch = lambda t: L.call("ecb200_knn_tc_f16", P(hh), P(hl), P(nb), P(xxs), P(cmax), B, C, N, k, P(idx), t, st)
 elif KIND == "xyz":
     rows = torch.empty(2, B * N, 64, device=dev, dtype=torch.float16); xxs = torch.empty(B * N, device=dev)
-    L.call("ecb200_pack_xyz_f16", P(x), B, C, N, P(rows[0]), P(rows[1]), P(xxs), st)
-    launch = lambda t: L.call("ecb200_knn_tc_xyz", P(rows[0]), P(rows[1]), P(xxs), B, N, k, P(idx), t, st)
+    cmax = torch.empty(B * ((N + 31) // 32), device=dev)
+    L.call("ecb200_pack_xyz_f16", P(x), B, C, N, P(rows[0]), P(rows[1]), P(xxs), P(cmax), st)
+    launch = lambda t: L.call("ecb200_knn_tc_xyz", P(rows[0]), P(rows[1]), P(xxs), P(cmax), B, N, k, P(idx), t, st)
 else:
     launch = lambda t: (L.call("ecb200_debug_tc_timeline", P(hi), P(lo), P(xx), B, C, N, k, P(idx), P(ws), t, st) if t is not None
                         else L.call("ecb200_knn_tc", P(hi), P(lo), P(xx), B, C, N, k, 1, P(idx), P(ws), nb, st))
