@@ -69,6 +69,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager-reference", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
+    ap.add_argument("--profile-ranks", action="store_true",
+                    help="multi-rank runs: also take the per-kernel profile of the replayed graph (rank 0 reports)")
     return ap.parse_args()
 
 
@@ -521,7 +523,9 @@ def run_b200(a):
 
     # ---- per-kernel time inside the replayed graph (after the timed regions; single-rank runs)
     kprof, kprof_err = None, None
-    if world == 1 and use_graph and not a.no_kernel_profile:
+    # (multi-rank: every rank replays -- the graph holds the exchanges -- and rank 0 reports; the statistics
+    # exchange kernels then show their wait for the slowest rank, i.e. where the scaling loss sits)
+    if use_graph and not a.no_kernel_profile and (world == 1 or a.profile_ranks):
         try:
             def replay(i):
                 flush.zero_()

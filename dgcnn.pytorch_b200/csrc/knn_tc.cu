@@ -45,6 +45,8 @@ constexpr uint32_t A_COL0 = 2 * BN;      // hi at columns [256, 256+C), lo at [2
 constexpr int UMMA_K = 8;                // tf32: 32 bytes of K per instruction
 constexpr int KMAX = 40;                 // largest k this kernel takes
 constexpr int GUARD = 16;                // candidate columns between two overflow checks of a survivor list
+constexpr int STG_LD = 36;               // dense-store variant: floats per staged row (32 + 4: conflict-free float4 access)
+constexpr int STG_SLOTS = 18;            // ... its staging area, in units of a survivor slot row (2 KB): 8 warps x 32 rows x 144 B
 
 struct SharedTail {  // lives after the operand ring and the survivor lists
   float hx[2][2][BN];              // [group][ping-pong] -0.5*|x_j|^2 of the current column tile
@@ -109,7 +111,7 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
   unsigned char* b_st = base;                                  // [S][32 KB]
   uint64_t* surv = reinterpret_cast<uint64_t*>(b_st + (size_t)S * STAGE_BYTES);   // [cap][256]
   SharedTail* T = reinterpret_cast<SharedTail*>(reinterpret_cast<unsigned char*>(surv) +
-                                                (size_t)(DEBUG ? 0 : cap) * LS * sizeof(uint64_t));
+                                                (size_t)(DEBUG ? STG_SLOTS : cap) * LS * sizeof(uint64_t));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, rt = blockIdx.x;
@@ -123,7 +125,7 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
 
   // epilogue threads fetch their query row (first 64 channels) before anything else: the loads
   // are in flight while the barriers are initialised and tensor memory is allocated
-  float4 pre[16];
+  float4 pre[16], pre2[16];   // words 0..63 and 64..127 of the row (the second half only when C > 64)
   if (warp >= 2) {
     const int g = (warp - 2) >> 2, q = warp & 3;
     const int row = rt * BM + q * 32 + lane;
@@ -132,6 +134,13 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
     for (int e = 0; e < 16; ++e) {
       pre[e] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < Na && 4 * e < C) pre[e] = __ldg(reinterpret_cast<const float4*>(src) + e);
+    }
+    if (C > 64) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        pre2[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < Na && 64 + 4 * e < C) pre2[e] = __ldg(reinterpret_cast<const float4*>(src) + 16 + e);
+      }
     }
   }
 
@@ -371,17 +380,21 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
           tmem_st_32x32(dst + (uint32_t)(h * 32), r);
         }
       }
-      for (int c0 = 64; c0 < C; c0 += 32) {
-        uint32_t r[32];
+      if (C > 64) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) f = __ldg(reinterpret_cast<const float4*>(src + c0) + e);
-          r[4 * e + 0] = __float_as_uint(f.x); r[4 * e + 1] = __float_as_uint(f.y);
-          r[4 * e + 2] = __float_as_uint(f.z); r[4 * e + 3] = __float_as_uint(f.w);
+        for (int h = 0; h < 2; ++h) {       // the prefetched second 64 words
+          if (64 + h * 32 < C) {
+            uint32_t r[32];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 f = pre2[8 * h + e];
+              r[4 * e + 0] = __float_as_uint(f.x); r[4 * e + 1] = __float_as_uint(f.y);
+              r[4 * e + 2] = __float_as_uint(f.z); r[4 * e + 3] = __float_as_uint(f.w);
+            }
+            __syncwarp();
+            tmem_st_32x32(dst + (uint32_t)(64 + h * 32), r);
+          }
         }
-        __syncwarp();
-        tmem_st_32x32(dst + (uint32_t)c0, r);
       }
       if (FOLD && TERMS == 3 && !DEBUG && g == 0) {
         // the query side of the norm block: 2^15 (0x7800) in its first three K slots, the same for every row
@@ -478,15 +491,29 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
             }
           }
           if (DEBUG) {  // dense store of the tile: raw scores, or the GEMM result Y = A.B^T
-            if (valid) {
-              float* orow = dbg + ((size_t)(a_row0 + row)) * N + ct * BN + c4 * 32;
-              if ((N & 3) == 0) {
+            if ((N & 3) == 0) {
+              // A thread holds 32 consecutive columns of ITS row: stored directly, one instruction would
+              // touch 32 rows with 16 bytes each.  The warp's 32 x 32 block goes through a private
+              // staging tile instead and leaves as full 128-byte lines, four rows per instruction.
+              float* stg = reinterpret_cast<float*>(surv) + (size_t)(warp - 2) * 32 * STG_LD;
+              __syncwarp();
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  if (ct * BN + c4 * 32 + 4 * e < N)
-                    *reinterpret_cast<float4*>(orow + 4 * e) =
-                        make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-              } else {
+              for (int e = 0; e < 8; ++e)
+                *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * e) =
+                    make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+              __syncwarp();
+              const int col = ct * BN + c4 * 32 + 4 * (lane & 7);
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int r = 4 * it + (lane >> 3);                  // row of the warp's block
+                const int grow = rt * BM + q * 32 + r;
+                const float4 w = *reinterpret_cast<const float4*>(stg + r * STG_LD + 4 * (lane & 7));
+                if (grow < Na && col < N)
+                  *reinterpret_cast<float4*>(dbg + ((size_t)(a_row0 + grow)) * N + col) = w;
+              }
+            } else if (valid) {
+              float* orow = dbg + ((size_t)(a_row0 + row)) * N + ct * BN + c4 * 32;
+              {
 #pragma unroll
                 for (int u = 0; u < 32; ++u)
                   if (ct * BN + c4 * 32 + u < N) orow[u] = v[u];
@@ -1012,7 +1039,7 @@ int launch_tc(const TcArgs& a, cudaStream_t st) {
   }
   const int nkb = a.C / KB;
   auto kern = knn_tc_kernel<32, DEBUG, CL, S, F16, TERMS, FOLD>;
-  constexpr size_t smem = smem_bytes(S, DEBUG ? 0 : CAP);
+  constexpr size_t smem = smem_bytes(S, DEBUG ? STG_SLOTS : CAP);
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static thread_local bool seen[ecb200::kMaxDevices] = {};
   if (ecb200::first_use_on_device(seen))

@@ -45,7 +45,7 @@ struct Finalize {
   float *dgamma, *dbeta, *c1, *c2;     // kind 2 outputs
 };
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 peer_allreduce_kernel(double* __restrict__ vals, int n, void* const* __restrict__ peer_bufs, int rank,
                       int world, unsigned long long* __restrict__ seq_counter, Finalize fin) {
   constexpr size_t MAXV = ECB200_PEER_MAX_VALUES;
@@ -66,14 +66,31 @@ peer_allreduce_kernel(double* __restrict__ vals, int n, void* const* __restrict_
   // 2. collect: a word is valid once it carries this exchange's sequence number; sum in rank order
   const unsigned long long* src = reinterpret_cast<const unsigned long long*>(peer_bufs[rank]) +
                                   (size_t)par * world * MAXV * 2;
+  // (the words of up to 8 peers are loaded before any of them is checked: one memory round trip per
+  // group instead of one per word -- at 8 ranks the serial form cost 16 dependent loads per value)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double acc = 0.0;
-    for (int q = 0; q < world; ++q) {
-      const unsigned long long* w = src + ((size_t)q * MAXV + i) * 2;
-      unsigned long long w0, w1;
-      while (((w0 = ld_volatile_u64(w)) & 0xffffffff00000000ull) != tag) __nanosleep(20);
-      while (((w1 = ld_volatile_u64(w + 1)) & 0xffffffff00000000ull) != tag) __nanosleep(20);
-      acc += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    for (int q0 = 0; q0 < world; q0 += 8) {
+      unsigned long long w0[8], w1[8];
+      bool pending = true;
+      while (pending) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (q0 + u < world) {
+            const unsigned long long* w = src + ((size_t)(q0 + u) * MAXV + i) * 2;
+            w0[u] = ld_volatile_u64(w);
+            w1[u] = ld_volatile_u64(w + 1);
+          }
+        pending = false;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (q0 + u < world)
+            pending |= ((w0[u] & 0xffffffff00000000ull) != tag) | ((w1[u] & 0xffffffff00000000ull) != tag);
+        if (pending) __nanosleep(20);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)   // rank order: bit-identical sums on every rank
+        if (q0 + u < world) acc += __longlong_as_double((long long)((w0[u] & 0xffffffffull) | (w1[u] << 32)));
     }
     vals[i] = acc;
   }
@@ -116,7 +133,7 @@ extern "C" int ecb200_peer_allreduce(double* vals, int n, void* const* peer_bufs
               ECB200_PEER_MAX_VALUES);
   ECB_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "ecb200_peer_allreduce: bad rank/world");
   Finalize fin = {};
-  peer_allreduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(vals, n, peer_bufs, rank, world, seq_counter, fin);
+  peer_allreduce_kernel<<<1, n > 512 ? 1024 : 512, 0, (cudaStream_t)stream>>>(vals, n, peer_bufs, rank, world, seq_counter, fin);
   ECB_LAUNCH_CHECK("peer_allreduce_kernel");
   return ECB200_OK;
 }
@@ -132,7 +149,7 @@ extern "C" int ecb200_peer_allreduce_bn_finalize(double* stats, int Co, void* co
   Finalize fin = {};
   fin.kind = 1; fin.Co = Co; fin.eps = eps; fin.gamma = gamma; fin.beta = beta;
   fin.mean = mean; fin.invstd = invstd; fin.a = a; fin.b = b;
-  peer_allreduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(stats, 2 * Co + 1, peer_bufs, rank, world, seq_counter, fin);
+  peer_allreduce_kernel<<<1, Co > 256 ? 1024 : 512, 0, (cudaStream_t)stream>>>(stats, 2 * Co + 1, peer_bufs, rank, world, seq_counter, fin);
   ECB_LAUNCH_CHECK("peer_allreduce_kernel<bn_finalize>");
   return ECB200_OK;
 }
@@ -149,7 +166,7 @@ extern "C" int ecb200_peer_allreduce_bwd_finalize(const double* bstats_local, do
   Finalize fin = {};
   fin.kind = 2; fin.Co = Co; fin.local = bstats_local; fin.count = count_dev; fin.a_in = a; fin.invstd_in = invstd;
   fin.dgamma = dgamma; fin.dbeta = dbeta; fin.c1 = c1; fin.c2 = c2;
-  peer_allreduce_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(bstats_global, 2 * Co, peer_bufs, rank, world, seq_counter, fin);
+  peer_allreduce_kernel<<<1, Co > 256 ? 1024 : 512, 0, (cudaStream_t)stream>>>(bstats_global, 2 * Co, peer_bufs, rank, world, seq_counter, fin);
   ECB_LAUNCH_CHECK("peer_allreduce_kernel<bwd_finalize>");
   return ECB200_OK;
 }

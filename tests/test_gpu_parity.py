@@ -384,8 +384,10 @@ def test_dgcnn_golden_eval(ec):
     assert_rel(y, g["eval_out"], what="eval out")
 
 
-def test_dgcnn_config1_shape_vs_oracle_on_same_graphs(ec):
-    """BASELINE config 1 shapes (N=1024, k=20, emb 1024) on a batch the CPU oracle
+@pytest.mark.parametrize("B,N,k", [(2, 1024, 20),      # BASELINE config 1
+                                   (1, 2048, 40)])     # config 2 / part-seg backbone shape (N=2048, k=40)
+def test_dgcnn_config_shapes_vs_oracle_on_same_graphs(ec, B, N, k):
+    """BASELINE config 1 / 2 shapes (N=1024, k=20 / N=2048, k=40; emb 1024) on a batch the CPU oracle
     finishes in seconds; the oracle is driven with OUR per-layer graphs so the EdgeConv
     arithmetic is compared exactly, and the graphs are compared separately.
 
@@ -395,11 +397,11 @@ def test_dgcnn_config1_shape_vs_oracle_on_same_graphs(ec):
     to cancellation, which tools/diag_precision.py shows is not an EdgeConv error.)
     Each quantity is also judged against the fp64 oracle."""
     torch.manual_seed(5)
-    args = SimpleNamespace(emb_dim=1024, k=20)
+    args = SimpleNamespace(emb_dim=1024, k=k)
     net = ec.DGCNN(args).to(dev()).train()
     net.record_idx = True
-    sd = {k: v.cpu() for k, v in net.state_dict().items()}
-    x = orc.synthetic_xyz(2, 1024, seed=1)
+    sd = {n: v.cpu() for n, v in net.state_dict().items()}
+    x = orc.synthetic_xyz(B, N, seed=1)
     xg = x.to(dev()).requires_grad_(True)
     y = net(xg)
     gout = torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
@@ -418,22 +420,27 @@ def test_dgcnn_config1_shape_vs_oracle_on_same_graphs(ec):
     y32, dx32, g32 = run_oracle(torch.float32)
     y64, dx64, g64 = run_oracle(torch.float64)
 
-    def judge(ours, r32, r64, what):
+    def judge(ours, r32, r64, what, flip_dim=None):
         ours, r32 = ours.detach().cpu().double(), r32.double()
         scale = r64.abs().max().item()
         e_ours = (ours - r64).abs().max().item()
         e_ref = (r32 - r64).abs().max().item()
         d = (ours - r32).abs().max().item()
         ok = d <= REL * scale or e_ours <= max(REL * scale, 2.0 * e_ref)
+        if not ok and flip_dim is not None:
+            # a near-tie of the max over k resolved to the other neighbour (see assert_rel_modulo_arg_flips):
+            # violations must stay confined to a handful of points / weight rows
+            assert_rel_modulo_arg_flips(ours, r64, flip_dim, 8, what=f"{what} (N={N}, k={k})")
+            return
         assert ok, (f"{what}: |ours-ref32| {d:.3e}, |ours-ref64| {e_ours:.3e}, "
                     f"|ref32-ref64| {e_ref:.3e}, scale {scale:.3e}")
 
     judge(y, y32, y64, "out")
-    judge(xg.grad, dx32, dx64, "dx")
+    judge(xg.grad, dx32, dx64, "dx", flip_dim=2)
     for n, p in net.named_parameters():
-        judge(p.grad, g32[n], g64[n], f"grad {n}")
+        judge(p.grad, g32[n], g64[n], f"grad {n}", flip_dim=0 if p.dim() > 1 else None)
     # layer-1 graph against the oracle's own kNN on the same input
-    rep = orc.knn_mismatch_report(x, idx_list[0], orc.knn_oracle(x, 20), rel_eps=TIE_EPS)
+    rep = orc.knn_mismatch_report(x, idx_list[0], orc.knn_oracle(x, k), rel_eps=TIE_EPS)
     assert rep["bad_rows"] == 0, rep
 
 
