@@ -572,9 +572,9 @@ def run_b200(a):
             if n.startswith("knn_tc2_kernel<"):          # 256-row variant: packed fp16 only, <TERMS>
                 is_xyz, is_f16 = n.rstrip(">").split("<")[-1].strip() == "1", True
             elif n.startswith("knn_tc_kernel<32, false") or n.startswith("knn_tc_kernel<32, 0"):
-                tail = n.rstrip(">").split(",")[-2:]
-                is_xyz = len(n.split(",")) >= 6 and tail[-1].strip() == "1"
-                is_f16 = len(n.split(",")) >= 6 and tail[0].strip() in ("true", "1")
+                targs = [t.strip() for t in n[n.index("<") + 1:n.rindex(">")].split(",")]   # NBINS, DEBUG, CL, S, F16, TERMS, FOLD
+                is_xyz = len(targs) >= 6 and targs[5] == "1"
+                is_f16 = len(targs) >= 5 and targs[4] in ("true", "1")
             else:
                 continue
             if is_xyz != xyz:
