@@ -857,7 +857,7 @@ __device__ __forceinline__ float f16_scale(unsigned amax_bits) {
   if (!(a > 0.f) || amax_bits >= 0x7f800000u) return 1.f;   // empty / all-zero / non-finite input
   int e;
   (void)frexpf(a, &e);                                      // a = m 2^e, m in [0.5, 1)
-  return ldexpf(1.f, 12 - e);
+  return ldexpf(1.f, min(12 - e, 100));   // (a tensor of denormals keeps a finite scale)
 }
 // -0.5 q = 2^15 * (p0 + p1 + p2) with FP16 pieces p (q = |s x_j|^2 <= 2^31): exact to 2^-33 relative
 __device__ __forceinline__ void norm_pieces(float q, __half (&p)[3]) {
