@@ -6,9 +6,10 @@ root:  ``import dgcnn_pytorch_b200 as ec``.
 """
 from . import _lib, ops
 from .dgcnn import DGCNN, edgeconv_block, get_graph_feature, knn, two_conv_edge_block
+from .hog import compute_hog_1x1
 from .model import ClsHead, DGCNN_cls, DGCNN_semseg, IOStream, PointNet, cal_loss
 from .ops import edgeconv
 from .runtime import GraphedTrainStep
 
-__all__ = ["DGCNN", "GraphedTrainStep", "DGCNN_cls", "DGCNN_semseg", "PointNet", "ClsHead", "IOStream", "cal_loss",
+__all__ = ["compute_hog_1x1", "DGCNN", "GraphedTrainStep", "DGCNN_cls", "DGCNN_semseg", "PointNet", "ClsHead", "IOStream", "cal_loss",
            "edgeconv", "edgeconv_block", "two_conv_edge_block", "get_graph_feature", "knn", "ops", "_lib"]

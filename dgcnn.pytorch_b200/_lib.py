@@ -61,10 +61,12 @@ SIGNATURES = {
     "ecb200_embed_gemm": (P, P, P, P, LL, I, I, P, P, P),
     "ecb200_two_conv_fwd": (P, P, P, P, F, P, P, P, I, I, I, I, I, P, P, P),
     "ecb200_embed_pool_bwd_dz": (P, P, P, P, P, P, P, P, F, I, I, I, P, P),
+    "ecb200_hog_1x1": (P, P, I, I, I, P, P, P),
 }
 
 # kernels each entry point enqueues (memsets are not counted)
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
+KERNELS_PER_CALL["ecb200_hog_1x1"] = 2
 KERNELS_PER_CALL["ecb200_reverse_graph"] = 1      # one CTA per cloud (3 kernels only when N counters exceed shared memory)
 
 # entry points that do not return an error code

@@ -349,6 +349,18 @@ int ecb200_two_conv_fwd(const float* Y, const int32_t* idx, const float* a1, con
                         int B, int N, int k, int C1, int C2, float* sel2, double* stats2, void* stream);
 
 #if defined(__GNUC__)
+/* ---- "next" row f-3: compute_hog_1x1 (models/model_partseg.py:15-92) on the device --------------
+ * x [B,3,N] (channel-major, as the reference holds it), idx [B,N,k] = knn(x, k) (cloud-local, any
+ * order) -> hist [B,N,18]: per point the L2-normalised 9-bin zenith and azimuth histograms (interleaved,
+ * [9][2]) of its neighbours' principal directions, weighted by the square root of the leading
+ * singular value.  Replaces the reference's device -> host copy + np.linalg.svd + host -> device copy.
+ * Bug-compatible with the reference's un-offset gathers (:28-30, :51-54: every cloud reads the first
+ * 3N floats of the batch and cloud 0's directions); the SIGN of each direction, which the reference
+ * inherits from LAPACK and which changes the zenith bin, is fixed to v_z >= 0 (ties: v_y, then v_x).
+ * dir_ws: N float4 of scratch (16-byte aligned). */
+int ecb200_hog_1x1(const float* x, const int32_t* idx, int B, int N, int k, float* dir_ws,
+                   float* hist, void* stream);
+
 #pragma GCC visibility pop
 #endif
 #ifdef __cplusplus

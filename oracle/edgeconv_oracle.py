@@ -233,6 +233,55 @@ def smoothed_ce_oracle(pred: torch.Tensor, gold: torch.Tensor, eps: float = 0.2)
 
 
 # ------------------------------------------------- synthetic inputs
+def hog_oracle(x: torch.Tensor, idx: torch.Tensor, canonical_sign: bool = False) -> torch.Tensor:
+    """compute_hog_1x1 (models/model_partseg.py:15-92) restated on the CPU, line by line, for a GIVEN
+    neighbour list ``idx`` [B,N,k] (the reference calls knn(x, k) itself, :26).  x [B,3,N] -> [B,N,18].
+
+    Kept bug-compatible: the gathers at :28-30 and :51-54 index a [B*N, 3] VIEW of the channel-major
+    memory with indices that carry no per-cloud offset, so every cloud reads rows 0..N-1 of that view
+    (the first 3N floats of the batch) and the gradients of cloud 0.
+
+    ``canonical_sign``: np.linalg.svd (:36) fixes the sign of each right singular vector by LAPACK's
+    internals, and the zenith angle acos(v_z) (:56) is NOT invariant under v -> -v.  With
+    canonical_sign the leading vector is flipped to v_z >= 0 (ties: v_y, then v_x): the convention the
+    GPU kernel (ecb200_hog_1x1) uses; without it this function is the reference bit for bit."""
+    import numpy as np
+    import torch.nn.functional as F
+    batch_size, num_pts, k = idx.shape
+    nn_idx = idx.reshape(-1)                                                       # :26
+    x_nn = x.contiguous().view(batch_size * num_pts, -1)[nn_idx, :].view(batch_size, num_pts, k, 3)   # :28-30
+    mean = x_nn.mean(dim=2, keepdim=True)                                          # :32
+    centered = x_nn - mean                                                         # :33
+    _, s, v = np.linalg.svd(centered.detach().cpu().numpy(), full_matrices=False)  # :36-37
+    if canonical_sign:
+        v0 = v[:, :, 0, :]
+        neg = (v0[..., 2] < 0) | ((v0[..., 2] == 0) & ((v0[..., 1] < 0) | ((v0[..., 1] == 0) & (v0[..., 0] < 0))))
+        v[:, :, 0, :] = np.where(neg[..., None], -v0, v0)
+    v = torch.from_numpy(v)                                                        # :39
+    s = torch.from_numpy(np.sqrt(s))                                               # :40
+    gradients = v[:, :, 0]                                                         # :49
+    magnitudes = s[:, :, 0].unsqueeze(-1)                                          # :50
+    gradients_nn = gradients.view(batch_size * num_pts, -1)[nn_idx, :].view(batch_size, num_pts, k, 3)    # :53-54
+    magnitudes_nn = magnitudes.view(batch_size * num_pts, -1)[nn_idx, :].view(batch_size, num_pts, k, 1)  # :55-56
+    zenith = torch.acos(gradients_nn[:, :, :, 2]).unsqueeze(-1) * 180 / np.pi      # :58
+    azimuth = torch.atan(gradients_nn[:, :, :, 1] / gradients_nn[:, :, :, 0]).unsqueeze(-1) * 180 / np.pi   # :59-60
+    cells = torch.cat((zenith.int(), azimuth.int(), magnitudes_nn), dim=-1)        # :62
+    cells[cells < 0] += 180                                                        # :64
+    histogram = torch.zeros((batch_size, num_pts, 9, 2))                           # :66-75
+    bins = torch.floor(cells[:, :, :, :2] / 20.0 - 0.5) % 9                        # :77
+    width = 20.0
+    num_bins = 9
+    first_centers = width * ((bins + 1) % num_bins + 0.5)                          # :81
+    first_votes = cells[:, :, :, 2].unsqueeze(-1) * ((first_centers - cells[:, :, :, :2]) % 180) / width   # :82-83
+    second_centers = width * (bins + 0.5)                                          # :85
+    second_votes = cells[:, :, :, 2].unsqueeze(-1) * ((cells[:, :, :, :2] - second_centers) % 180) / width  # :86-87
+    for c in range(9):                                                             # :88-90
+        histogram[:, :, c] += (first_votes * (bins == c)).sum(dim=2)
+        histogram[:, :, (c + 1) % 9] += (second_votes * (bins == c)).sum(dim=2)
+    histogram = F.normalize(histogram, p=2.0, dim=2)                               # :91
+    return histogram.view(batch_size, num_pts, -1)                                 # :92-93
+
+
 def synthetic_xyz(B: int, N: int, seed: int = 1, device="cpu") -> torch.Tensor:
     """ModelNet40-shape clouds: centred, scaled into the unit ball, [B,3,N]."""
     g = torch.Generator().manual_seed(seed)

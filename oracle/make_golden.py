@@ -212,6 +212,25 @@ def case_two_conv_block():
         **{f"sd.{k_}": v for k_, v in sd.items()})
 
 
+def case_hog():
+    """compute_hog_1x1 (models/model_partseg.py:15-92, row f-3): the restatement must equal the
+    unmodified reference bit for bit (use_cpu=True keeps the reference on the CPU); the fixture also
+    stores the canonical-sign variant the GPU kernel is compared with."""
+    sys.path.insert(0, REF)
+    import models.model_partseg as ps
+    sys.path.pop(0)
+    for tag, B, N, k, seed in (("B2_N64_k8", 2, 64, 8, 21), ("B3_N200_k20", 3, 200, 20, 22)):
+        x = orc.synthetic_xyz(B, N, seed=seed)
+        ref_h = ps.compute_hog_1x1(x, k, use_cpu=True)
+        idx = orc.knn_oracle(x, k)
+        mine = orc.hog_oracle(x, idx, canonical_sign=False)
+        assert torch.equal(ref_h, mine), f"hog {tag}: restatement differs from the reference"
+        canon = orc.hog_oracle(x, idx, canonical_sign=True)
+        flipped = float(((ref_h - canon).abs().amax(-1) > 1e-6).float().mean())
+        print(f"hog {tag}: reference == restatement; canonical sign changes {100 * flipped:.1f} % of the points' histograms")
+        npz(f"hog_{tag}.npz", x=x, k=k, idx=idx.to(torch.int32), hog_reference=ref_h, hog_canonical=canon)
+
+
 def main():
     torch.set_num_threads(1)        # deterministic reduction order
     os.makedirs(GOLD, exist_ok=True)
@@ -221,6 +240,7 @@ def main():
     case_block(ref)
     case_dgcnn(ref)
     case_two_conv_block()
+    case_hog()
     print("oracle == reference on every case; fixtures written")
 
 

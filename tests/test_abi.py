@@ -113,6 +113,10 @@ def test_argument_validation_of_the_fp16_knn_entry_points(ec):
         call("ecb200_absmax", one, 0, one, None)
     with pytest.raises(RuntimeError, match="null pointer"):
         call("ecb200_edge_apply_amax", None, one, one, 0.2, 1, 8, 8, one, None, 8, one, None)
+    with pytest.raises(RuntimeError, match="bad shape"):
+        call("ecb200_hog_1x1", one, one, 1, 8, 9, one, one, None)          # k > N
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        call("ecb200_hog_1x1", one, one, 1, 8, 4, ctypes.c_void_p(20), one, None)
     assert ec.ops.AMAX_SLOTS == 32
     # kernel choice of knn(): packed fp16 for C % 64 == 0, tf32 halves for the other multiples of 32, the
     # one-K-step kernel for xyz-like inputs, FP32 FMA for everything else

@@ -166,3 +166,19 @@ def test_two_conv_edge_block_matches_reference():
     assert torch.equal(x.grad, g["dx"])
     assert torch.equal(b1[0].weight.grad, g["dw1"]) and torch.equal(b2[0].weight.grad, g["dw2"])
     assert torch.equal(b2[1].weight.grad, g["dgamma2"]) and torch.equal(b2[1].bias.grad, g["dbeta2"])
+
+
+@pytest.mark.parametrize("name", ["hog_B2_N64_k8.npz", "hog_B3_N200_k20.npz"])
+def test_hog_oracle_equals_the_recorded_reference(name):
+    """compute_hog_1x1 (models/model_partseg.py:15-92, row f-3): the restatement reproduces what the unmodified
+    reference returned (recorded by oracle/make_golden.py with use_cpu=True) bit for bit, and the
+    canonical-sign variant -- the GPU kernel's convention -- is reproducible too."""
+    g = load_golden(name)
+    h = orc.hog_oracle(g["x"], g["idx"].long(), canonical_sign=False)
+    assert torch.equal(h, g["hog_reference"])
+    hc = orc.hog_oracle(g["x"], g["idx"].long(), canonical_sign=True)
+    assert torch.equal(hc, g["hog_canonical"])
+    assert tuple(h.shape) == (g["x"].shape[0], g["x"].shape[2], 18)
+    # every histogram is L2-normalised per angle type (or all zero)
+    n = hc.view(*hc.shape[:2], 9, 2).norm(dim=2)
+    assert bool(((n - 1).abs() < 1e-5).logical_or(n == 0).all())
