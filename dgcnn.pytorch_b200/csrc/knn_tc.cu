@@ -175,8 +175,9 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
       constexpr int SLICE_ROWS = BM / CL;                 // rows of every tile this CTA fetches
       const uint32_t slice_off = crank * (uint32_t)(SLICE_ROWS * KB * 4);
       auto load = [&](unsigned char* dst, const CUtensorMap* m, uint64_t* bar, int c0, int r0) {
-        if (CL > 1) tma_load_2d_mc(dst + slice_off, m, bar, c0, r0 + (int)crank * SLICE_ROWS, CMASK);
-        else        tma_load_2d(dst, m, bar, c0, r0);
+        if (FOLD && !DEBUG) tma_load_3d(dst, m, bar, c0, r0 - cloud_row0, b);   // per-cloud map: rows past N are NaN
+        else if (CL > 1)    tma_load_2d_mc(dst + slice_off, m, bar, c0, r0 + (int)crank * SLICE_ROWS, CMASK);
+        else                tma_load_2d(dst, m, bar, c0, r0);
       };
       if (!DEBUG && FOLD && TERMS == 3) {
         // first sweep: nkb hi K-blocks + the norm block of every tile, two blocks per stage
@@ -471,15 +472,10 @@ knn_tc_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_g
           const float4* hx4 = reinterpret_cast<const float4*>(hx + c4 * 32);
           float v[32];
           if (FOLD && !DEBUG) {
-            // the accumulator already is the score; only the ragged last tile needs its columns past the
-            // end of the cloud masked (warp-uniform branch)
+            // the accumulator already is the score; candidates past the end of the cloud were loaded as NaN
+            // (per-cloud tensor map with NaN fill) and score NaN: fmaxf drops them, >= rejects them
 #pragma unroll
             for (int u = 0; u < 32; ++u) v[u] = __uint_as_float(cur[u]);
-            if ((ct + 1) * BN > N) {
-#pragma unroll
-              for (int u = 0; u < 32; ++u)
-                if (ct * BN + c4 * 32 + u >= N) v[u] = -CUDART_INF_F;
-            }
           } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -1030,11 +1026,17 @@ struct TcArgs {
 template <bool DEBUG, int CL, int S, int CAP, bool F16 = false, int TERMS = 3, bool FOLD = false>
 int launch_tc(const TcArgs& a, cudaStream_t st) {
   OperandMaps Bm;
-  int rc = make_operand(&Bm, a.b_hi, a.b_lo, a.b_rows, a.C, BM / CL);
+  int rc;
+  if (FOLD && !DEBUG) {   // per-cloud maps: candidate rows past the end of a cloud read as NaN
+    rc = make_cloud_map(&Bm.hi, a.b_hi, a.clouds, a.Nb, a.C, BM);
+    if (!rc) rc = make_cloud_map(&Bm.lo, a.b_lo, a.clouds, a.Nb, a.C, BM);
+  } else {
+    rc = make_operand(&Bm, a.b_hi, a.b_lo, a.b_rows, a.C, BM / CL);
+  }
   if (rc) return rc;
   CUtensorMap Bn = Bm.hi;   // placeholder unless the norm block is a separate operand
   if (FOLD && TERMS == 3) {
-    rc = make_point_map(&Bn, a.bn, a.b_rows, KB, BM / CL);
+    rc = make_cloud_map(&Bn, a.bn, a.clouds, a.Nb, KB, BM);
     if (rc) return rc;
   }
   const int nkb = a.C / KB;

@@ -138,7 +138,7 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
             unsigned char* dst = b_st + (size_t)stage * STAGE_BYTES;
             mbar_expect_tx(&T->b_full[stage], kpa * TILE_BYTES);
             for (int j = 0; j < kpa; ++j)
-              tma_load_2d(dst + j * TILE_BYTES, &map_bhi, &T->b_full[stage], (kb + j) * KB, cloud_row0 + ct * BN);
+              tma_load_3d(dst + j * TILE_BYTES, &map_bhi, &T->b_full[stage], (kb + j) * KB, ct * BN, b);
           }
           __syncwarp();
           advance();
@@ -157,8 +157,8 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
             unsigned char* dst = b_st + (size_t)stage * STAGE_BYTES;
             mbar_expect_tx(&T->b_full[stage], nun * TILE_BYTES);
             for (int j = 0; j < nun; ++j) {
-              if (u0 + j < nkb) tma_load_2d(dst + j * TILE_BYTES, &map_bhi, &T->b_full[stage], (u0 + j) * KB, cloud_row0 + ct * BN);
-              else              tma_load_2d(dst + j * TILE_BYTES, &map_bn, &T->b_full[stage], 0, cloud_row0 + ct * BN);
+              if (u0 + j < nkb) tma_load_3d(dst + j * TILE_BYTES, &map_bhi, &T->b_full[stage], (u0 + j) * KB, ct * BN, b);
+              else              tma_load_3d(dst + j * TILE_BYTES, &map_bn, &T->b_full[stage], 0, ct * BN, b);
             }
           }
           __syncwarp();
@@ -172,11 +172,11 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
             unsigned char* dst = b_st + (size_t)stage * STAGE_BYTES;
             if (kb < nkb) {
               mbar_expect_tx(&T->b_full[stage], 2 * TILE_BYTES);
-              tma_load_2d(dst, &map_bhi, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
-              tma_load_2d(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, cloud_row0 + ct * BN);
+              tma_load_3d(dst, &map_bhi, &T->b_full[stage], kb * KB, ct * BN, b);
+              tma_load_3d(dst + TILE_BYTES, &map_blo, &T->b_full[stage], kb * KB, ct * BN, b);
             } else {
               mbar_expect_tx(&T->b_full[stage], TILE_BYTES);
-              tma_load_2d(dst, &map_bn, &T->b_full[stage], 0, cloud_row0 + ct * BN);
+              tma_load_3d(dst, &map_bn, &T->b_full[stage], 0, ct * BN, b);
             }
           }
           __syncwarp();
@@ -335,16 +335,11 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
         mbar_wait(&T->t_full[g], use & 1);
         tc_fence_after();
         auto process = [&](uint32_t(&cur)[32], const int c2, const bool second_pass) {
-          // the accumulator already is the score; only the ragged last tile needs the columns past the
-          // end of the cloud masked (warp-uniform branch)
+          // the accumulator already is the score; candidates past the end of the cloud were loaded as NaN
+          // (per-cloud tensor map with NaN fill) and score NaN: fmaxf drops them, >= rejects them
           float v[32];
 #pragma unroll
           for (int u = 0; u < 32; ++u) v[u] = __uint_as_float(cur[u]);
-          if ((ct + 1) * BN > N) {
-#pragma unroll
-            for (int u = 0; u < 32; ++u)
-              if (ct * BN + c2 * 32 + u >= N) v[u] = -CUDART_INF_F;
-          }
           if (!second_pass) {
 #pragma unroll
             for (int u = 0; u < 32; ++u) bin[u] = fmaxf(bin[u], v[u]);
@@ -532,12 +527,13 @@ knn_tc2_kernel(const float* __restrict__ a_hi_g, const float* __restrict__ a_lo_
 
 template <int TERMS>
 int launch(const ecb200::knntc::Tc2Args& a, cudaStream_t st) {
-  OperandMaps Bm;
-  int rc = make_operand(&Bm, a.b_hi, a.b_lo, a.b_rows, a.Cw, BN);
+  OperandMaps Bm;   // per-cloud maps: candidate rows past the end of a cloud read as NaN
+  int rc = make_cloud_map(&Bm.hi, a.b_hi, a.clouds, a.N, a.Cw, BN);
+  if (!rc) rc = make_cloud_map(&Bm.lo, a.b_lo, a.clouds, a.N, a.Cw, BN);
   if (rc) return rc;
   CUtensorMap Bn = Bm.hi;   // placeholder unless the norm block is a separate operand
   if (TERMS == 3) {
-    rc = make_point_map(&Bn, a.bn, a.b_rows, KB, BN);
+    rc = make_cloud_map(&Bn, a.bn, a.clouds, a.N, KB, BN);
     if (rc) return rc;
   }
   auto kern = knn_tc2_kernel<TERMS>;

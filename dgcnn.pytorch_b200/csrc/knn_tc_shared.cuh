@@ -102,6 +102,29 @@ inline int make_point_map(CUtensorMap* m, const float* p, long long rows, int C,
   return ECB200_OK;
 }
 
+// [clouds, N, C] fp32 row-major as a 3-D map, box = 32 channels x box_rows rows of ONE cloud, 128-byte swizzle;
+// rows past the end of a cloud read as NaN: a candidate that does not exist scores NaN, which no
+// comparison of the selector accepts (fmaxf drops it, >= is false) -- no masking code in the epilogue
+inline int make_cloud_map(CUtensorMap* m, const float* p, int clouds, int N, int C, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) {
+    ecb200::set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return ECB200_ERR_CUDA;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)clouds};
+  const cuuint64_t strides[2] = {(cuuint64_t)C * sizeof(float), (cuuint64_t)N * C * sizeof(float)};
+  const cuuint32_t box[3] = {KB, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+  if (r != CUDA_SUCCESS) {
+    ecb200::set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+    return ECB200_ERR_CUDA;
+  }
+  return ECB200_OK;
+}
+
 // [rows, C] fp32 row-major operand pair (hi, lo) as TMA maps
 struct OperandMaps {
   CUtensorMap hi, lo;

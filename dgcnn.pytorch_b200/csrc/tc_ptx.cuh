@@ -70,6 +70,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// 3-D tile load (channel block, row in the cloud, cloud): rows past the end of a cloud are out of bounds
+// of the middle dimension, so the map's fill value (NaN for the kNN candidates) lands there
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ---- TMEM ---------------------------------------------------------------------------
 template <uint32_t COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem) {  // one full warp
