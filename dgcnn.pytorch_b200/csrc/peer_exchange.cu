@@ -73,6 +73,7 @@ peer_allreduce_kernel(double* __restrict__ vals, int n, void* const* __restrict_
     for (int q0 = 0; q0 < world; q0 += 8) {
       unsigned long long w0[8], w1[8];
       bool pending = true;
+      unsigned spins = 0;
       while (pending) {
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -86,7 +87,15 @@ peer_allreduce_kernel(double* __restrict__ vals, int n, void* const* __restrict_
         for (int u = 0; u < 8; ++u)
           if (q0 + u < world)
             pending |= ((w0[u] & 0xffffffff00000000ull) != tag) | ((w1[u] & 0xffffffff00000000ull) != tag);
-        if (pending) __nanosleep(20);
+        if (pending) {
+          __nanosleep(20);
+          // a peer that never arrives (crashed rank) must not hang the GPU: after ~2^22 polls (seconds)
+          // give up and poison the value -- the step's loss turns NaN instead of the device wedging
+          if (++spins > (1u << 22)) {
+            acc = __longlong_as_double(0x7ff8000000000000LL);
+            break;
+          }
+        }
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u)   // rank order: bit-identical sums on every rank

@@ -15,7 +15,12 @@ except Exception as e:
 PY
 }
 run n8_weak 8
+run n2_weak 2
 run n4_weak 4
 run n8_strong 8 --scaling strong
 run n8_cfg2_strong 8 --scaling strong --points 2048 --k 40
-run n8_cfg2_weak 8 --points 2048 --k 40 --batch 4
+# single-GPU line of the same build on the same box, for the ratio
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-reference > gpurun_out/n1_same_box.json 2> gpurun_out/n1_same_box.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/n1_same_box.json').read().strip().splitlines()[-1]); print('n1_same_box: value %.0f  %.3f ms/step' % (d['value'], d['ms_per_step']))"
