@@ -62,6 +62,8 @@ SIGNATURES = {
     "ecb200_two_conv_fwd": (P, P, P, P, F, P, P, P, I, I, I, I, I, P, P, P),
     "ecb200_embed_pool_bwd_dz": (P, P, P, P, P, P, P, P, F, I, I, I, P, P),
     "ecb200_hog_1x1": (P, P, I, I, I, P, P, P),
+    "ecb200_rows_bn_bwd_stats": (P, P, P, P, I, I, P, P, P, P),
+    "ecb200_rows_bn_bwd_dx": (P, P, P, P, P, P, P, I, I, P, P),
 }
 
 # kernels each entry point enqueues (memsets are not counted)

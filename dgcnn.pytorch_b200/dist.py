@@ -92,6 +92,8 @@ class FlatGradSync:
             o += p.numel()
         n_late = sum(p.numel() for p in self.late_ps)
         self.flat_late, self.flat_early = self.flat[:n_late], self.flat[n_late:]
+        # NCCL averages inside the collective (no separate scaling kernel); other backends sum, then scale
+        self._avg = bool(self.world > 1 and dist.get_backend(group) == "nccl" and hasattr(dist.ReduceOp, "AVG"))
         self.overlap = bool(overlap and self.world > 1 and self.early_ps and dev.type == "cuda")
         self._pending = len(self.early_ps)
         self._left = self._pending
@@ -119,9 +121,15 @@ class FlatGradSync:
             cur = torch.cuda.current_stream()
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
-                dist.all_reduce(self.flat_early, op=dist.ReduceOp.SUM, group=self.group)
-                self.flat_early.mul_(1.0 / self.world)
+                self._reduce_mean(self.flat_early)
             self._early_done = True
+
+    def _reduce_mean(self, buf: torch.Tensor) -> None:
+        if self._avg:
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            buf.mul_(1.0 / self.world)
 
     def zero(self) -> None:
         """start of a step: every ``.grad`` is None, so autograd stores (not accumulates) gradients"""
@@ -134,14 +142,12 @@ class FlatGradSync:
         if self._early_done:
             self._pack(self.late_ps)
             if self.flat_late.numel():
-                dist.all_reduce(self.flat_late, op=dist.ReduceOp.SUM, group=self.group)
-                self.flat_late.mul_(1.0 / self.world)
+                self._reduce_mean(self.flat_late)
             torch.cuda.current_stream().wait_stream(self._side)
         else:   # no overlap (or a hook did not fire): pack and reduce everything here
             self._pack(self.params)
             if self.world > 1:
-                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-                self.flat.mul_(1.0 / self.world)
+                self._reduce_mean(self.flat)
         for p in self.params:
             p.grad = self.view[p]
 

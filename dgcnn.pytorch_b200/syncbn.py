@@ -45,19 +45,25 @@ class _SyncBNRows(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, affine, stats = ctx.saved_tensors
-        F = x.shape[1]
-        mean, invstd, a = affine[0], affine[1], affine[2]
+        M, F = x.shape
+        dev = x.device
         g = g.contiguous().float()
-        xhat = (x - mean) * invstd
-        local = torch.cat([g.sum(0, dtype=torch.float64), (g * xhat).sum(0, dtype=torch.float64)])
-        total = local
-        if ctx.group:
-            total = local.clone()
-            ops._allreduce_stats(total, ctx.group)
-        n = stats[2 * F]
-        c = (total / n).float()
-        dx = a * (g - c[:F] - xhat * c[F:])
-        return dx, local[F:].float(), local[:F].float(), None, None, None, None, None, None
+        with torch.cuda.device(dev):
+            st = ops._stream(x)
+            mean, invstd, a = (c_void_p(affine.data_ptr() + 4 * F * r) for r in range(3))
+            total = torch.empty(2 * F, device=dev, dtype=torch.float64)
+            dgamma = torch.empty(F, device=dev, dtype=torch.float32)
+            dbeta = torch.empty(F, device=dev, dtype=torch.float32)
+            dx = torch.empty_like(x)
+            # local sums (also the parameter gradients) -> exchange -> dx: three launches
+            _lib.call("ecb200_rows_bn_bwd_stats", ops._ptr(g), ops._ptr(x), mean, invstd, M, F, ops._ptr(total),
+                      ops._ptr(dgamma), ops._ptr(dbeta), st)
+            if ctx.group:
+                ops._allreduce_stats(total, ctx.group)
+            count = c_void_p(stats.data_ptr() + 8 * 2 * F)          # stats[2F] = global row count (fp64)
+            _lib.call("ecb200_rows_bn_bwd_dx", ops._ptr(g), ops._ptr(x), mean, invstd, a, ops._ptr(total), count,
+                      M, F, ops._ptr(dx), st)
+        return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
 def batch_norm_rows(x: torch.Tensor, bn: nn.Module) -> torch.Tensor:

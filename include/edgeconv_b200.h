@@ -349,6 +349,17 @@ int ecb200_two_conv_fwd(const float* Y, const int32_t* idx, const float* a1, con
                         int B, int N, int k, int C1, int C2, float* sel2, double* stats2, void* stream);
 
 #if defined(__GNUC__)
+/* Backward of BatchNorm over the rows of a small [M,F] activation (the cls head's bn6 / bn7 under
+ * SyncBatchNorm), two launches around the statistics exchange:
+ *   ecb200_rows_bn_bwd_stats: total[2F] fp64 = [sum_m g | sum_m g*xhat] (the vector that is all-reduced),
+ *                             dbeta / dgamma [F] = the same sums in fp32 (local parameter gradients)
+ *   ecb200_rows_bn_bwd_dx:    dx = a * (g - total[f]/n - xhat * total[F+f]/n), n = *count (device fp64) */
+int ecb200_rows_bn_bwd_stats(const float* g, const float* x, const float* mean, const float* invstd,
+                             int M, int F, double* total, float* dgamma, float* dbeta, void* stream);
+int ecb200_rows_bn_bwd_dx(const float* g, const float* x, const float* mean, const float* invstd,
+                          const float* a, const double* total, const double* count, int M, int F,
+                          float* dx, void* stream);
+
 /* ---- "next" row f-3: compute_hog_1x1 (models/model_partseg.py:15-92) on the device --------------
  * x [B,3,N] (channel-major, as the reference holds it), idx [B,N,k] = knn(x, k) (cloud-local, any
  * order) -> hist [B,N,18]: per point the L2-normalised 9-bin zenith and azimuth histograms (interleaved,

@@ -344,6 +344,25 @@ def test_block_no_grad_and_inference_mode(ec):
     assert_rel(y, g["eval_out"], what="eval out (no_grad)")
 
 
+def test_operand_scale_side_channel_is_invalidated_by_in_place_writes(ec):
+    """edgeconv() measures max|out| while writing it and hands it to the next layer's fp16 operand kernel
+    (ops.known_amax).  The tag must die with any in-place change of the tensor: a stale scale would push
+    the scaled features out of fp16's range and wreck the next graph."""
+    torch.manual_seed(3)
+    d = dev()
+    x = orc.synthetic_features(2, 64, 512, seed=8).to(d)
+    block = ec.dgcnn._edge_block(128, 64).to(d).train()
+    with torch.no_grad():
+        out, _ = ec.edgeconv_block(x, block, 20)
+        tag = ec.ops.known_amax(out)
+        assert tag is not None and abs(float(tag.max()) - float(out.abs().max())) <= 1e-6 * float(out.abs().max())
+        out.mul_(4096.0)                                   # in place: the version counter moves
+        assert ec.ops.known_amax(out) is None
+        _, idx = ec.edgeconv_block(out, block, 20)         # graph of the modified tensor
+    rep = orc.knn_mismatch_report(out.cpu(), idx.long().cpu(), orc.knn_oracle(out.cpu(), 20), rel_eps=TIE_EPS)
+    assert rep["bad_rows"] == 0, rep
+
+
 # ------------------------------------------------------------------ the backbone
 def _dgcnn_pair(ec, g):
     args = SimpleNamespace(emb_dim=g["emb_dim"], k=g["k"])
