@@ -109,7 +109,10 @@ class FlatGradSync:
         that received no gradient contributes zeros"""
         have = [p for p in ps if p.grad is not None and p.grad.data_ptr() != self.view[p].data_ptr()]
         if have:
-            torch._foreach_copy_([self.view[p] for p in have], [p.grad for p in have])
+            # flattened on both sides: a 1x1-conv weight gradient in channels-last strides has the same element
+            # order as the contiguous slice, and differing strides would push the multi-tensor copy onto its
+            # slow per-tensor path (one un-vectorised 2 MB copy for conv5's weight)
+            torch._foreach_copy_([self.view[p].view(-1) for p in have], [p.grad.reshape(-1) for p in have])
         for p in ps:
             if p.grad is None:
                 self.view[p].zero_()
