@@ -1,18 +1,25 @@
-// Tensor-core kNN for the feature-space layers (C = 32..128 channels).
+// Tensor-core kNN (128 query rows per CTA): feature-space layers and, through the same pipeline, the xyz layer.
 //
 // The reference's knn() (models/dgcnn.py:6-12) is a dense contraction x^T x followed by a
 // row-wise top-k.  Here the contraction runs on the 5th-generation tensor cores:
-//   * operands are point-major [M, C] fp32 split into hi = tf32(x) and lo = tf32(x - hi)
-//     (ecb200_split_tf32); a tile of 128 points x 32 channels is one TMA box landing in
-//     shared memory in the canonical K-major SWIZZLE_128B layout;
-//   * D[128 queries x 128 candidates] += Ahi.Bhi^T + Ahi.Blo^T + Alo.Bhi^T  (3xTF32 error
-//     compensation, kind::tf32, FP32 accumulators in TMEM) -- one elected thread issues;
+//   * operands are point-major [M, C] split into hi + lo halves with 11-bit significands: PACKED FP16
+//     pairs of the tensor scaled by a power of two (ecb200_split_f16, kind::f16: twice the MMA rate, the
+//     default for C = 64 / 128) or tf32 values (ecb200_split_tf32, kind::tf32: C = 32 / 96).  A tile of
+//     128 points x 32 words is one TMA box landing in shared memory in the canonical K-major
+//     SWIZZLE_128B layout; in words the two operand types look the same to the kernel;
+//   * D[128 queries x 128 candidates] += Ahi.Bhi^T + Ahi.Blo^T + Alo.Bhi^T  (error-compensated product,
+//     FP32 accumulators in TMEM) -- one elected thread issues; with packed FP16 the column term
+//     -0.5*|x_j|^2 is three more K slots of the same contraction (FOLD), so the accumulator is the score;
 //   * two epilogue warpgroups (one per TMEM accumulator stage) read the accumulators with
-//     tcgen05.ld (lane = query row), add the -0.5*|x_j|^2 column term and feed the two-pass
-//     selector of topk_select.cuh, so the distance matrix never leaves the SM; MMAs of the
-//     next tile overlap the selection of the current one.
-// The query tile (A) stays resident in shared memory; candidate tiles (B) stream through a
-// TMA / mbarrier ring.  Pass A and pass B of the selector are two sweeps of the same MMAs.
+//     tcgen05.ld (lane = query row) and feed the two-pass selector of topk_select.cuh, so the distance
+//     matrix never leaves the SM; MMAs of the next tile overlap the selection of the current one;
+//   * xyz layer (C <= 4): the three product terms and the column term of a point sit in ONE 16-deep K
+//     step (TERMS = 1), one MMA per tile and sweep.
+// The query tile (A) is copied once into tensor memory (TS-mode MMAs); candidate tiles (B) stream through a
+// TMA / mbarrier ring, for the packed-FP16 kernels through per-cloud 3-D maps whose out-of-range rows read
+// as NaN (a candidate that does not exist can never be selected).  Pass A and pass B of the selector are
+// two sweeps of the same tiles.  The dense-store variant (DEBUG) of this kernel is the per-point GEMM
+// Y = X.Wcat^T of the EdgeConv layers.  knn_tc2.cu is the 256-row sibling.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
