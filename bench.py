@@ -592,8 +592,13 @@ def run_b200(a):
         # `peak` / `frac` follow SURVEY 8d's definition of this kernel's roofline (fp32-equivalent products on the
         # tensor pipe = TF32 peak / 3), the yardstick of round 1; the kernel now reaches the same accuracy with
         # kind::f16 MMAs, whose pipe peak is twice that: `frac_of_f16x3_pipe` is the fraction of the pipe in use
+        knn_traffic = None
+        kpath = os.path.join(ROOT, "profiles", "r2c_knn_traffic.json")
+        if (a.batch, a.points, a.k) == (32, 1024, 20) and os.path.exists(kpath):
+            with open(kpath) as f:
+                knn_traffic = json.load(f).get("dram_bytes_per_step")     # ncu --set full, DRAM read + write per step
         roof = {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": ach, "peak": tf32x3_peak,
-                "unit": "TFLOP/s", "frac": ach / tf32x3_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / tf32x3_peak, "traffic": knn_traffic,
                 "operands": ("packed fp16 hi/lo halves (kind::f16, 3 MMAs per product: same 11-bit significands and "
                              "error bound as 3xTF32 at twice the pipe rate)") if knn_f16 else "tf32 hi/lo halves (3xTF32)",
                 "peak_source": pk["source"] + " bf16 burst / 2 (tf32) / 3 (3xTF32), SURVEY 8d",
