@@ -205,16 +205,25 @@ __global__ void graph_feature_kernel(const float* __restrict__ x, const int32_t*
   const float* xb = x + (size_t)bb * C * N;
   if (mode == ECB200_GF_KNN_ONLY) {
     float* o = out + ((size_t)bb * NK + e) * C;
-    for (int c = 0; c < C; ++c) o[c] = xb[(size_t)c * N + nj];
+    if ((C & 3) == 0) {   // a thread's C outputs are contiguous: four gathered channels per 16-byte store
+#pragma unroll 4
+      for (int c = 0; c < C; c += 4)
+        *reinterpret_cast<float4*>(o + c) = make_float4(xb[(size_t)c * N + nj], xb[(size_t)(c + 1) * N + nj],
+                                                         xb[(size_t)(c + 2) * N + nj], xb[(size_t)(c + 3) * N + nj]);
+    } else {
+      for (int c = 0; c < C; ++c) o[c] = xb[(size_t)c * N + nj];
+    }
     return;
   }
   if (mode == ECB200_GF_DISP_ONLY) {
     float* o = out + (size_t)bb * C * NK + e;
+#pragma unroll 8   // independent gathers in flight: the loop is latency-bound otherwise
     for (int c = 0; c < C; ++c) o[(size_t)c * NK] = xb[(size_t)c * N + nj] - xb[(size_t)c * N + n];
     return;
   }
   float* o = out + (size_t)bb * 2 * C * NK + e;
   const bool centered = mode == ECB200_GF_CONCAT_CENTERED;
+  // (left to the compiler's own unrolling: forcing 8 halved this loop's throughput, measured)
   for (int c = 0; c < C; ++c) {
     const float xi = xb[(size_t)c * N + n];
     const float xj = xb[(size_t)c * N + nj];
